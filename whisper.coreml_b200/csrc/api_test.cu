@@ -1,0 +1,76 @@
+// Test hooks exported through the C ABI (tests/ only; see include/whisper_b200.h).
+#include "gemm.cuh"
+#include "ops.cuh"
+#include "whisper_b200.h"
+#include "decoder_step.cuh"
+
+using namespace b200;
+
+extern "C" void b200TestGemm(const void* dA, const void* dB, const float* dBias, void* dC, int M, int N, int K,
+                             int out_fp32, int gelu, int use_simt) {
+    if (use_simt) {
+        gemm_simt((const bf16*)dA, (const bf16*)dB, dBias, dC, M, N, K, out_fp32, gelu, 0);
+    } else {
+        GemmParams p = gemm_plain((const bf16*)dA, (const bf16*)dB, dC, M, N, K);
+        p.bias = dBias; p.gelu = gelu; p.c_fp32 = out_fp32;
+        gemm_tcgen05(p, 0);
+    }
+    B200_CHECK(cudaStreamSynchronize(0));
+}
+
+// ---- state read-back hooks (tests only) ---------------------------------------------------------
+#include <vector>
+#include "state.cuh"
+
+// Xa of window w as fp32 (1500, d) on the host.
+extern "C" void b200TestGetXa(float* out, int w) {
+    State& s = S();
+    if (!s.xa || w < 0 || w >= s.w_cap) { record_error("b200TestGetXa: no encoder output for window %d", w); return; }
+    const size_t n = (size_t)N_AUDIO_CTX * s.d;
+    float* tmp = nullptr;
+    if (!dev_alloc(&tmp, n)) return;
+    bf16_to_f32(s.xa + w * n, tmp, (long)n, s.stream);
+    B200_CHECK(cudaMemcpy(out, tmp, n * sizeof(float), cudaMemcpyDeviceToHost));
+    dev_free(&tmp);
+}
+
+// CK (Ld,H,64,1500) [pre-transposed like decoder.py:183] and CV (Ld,H,1500,64) of window w as fp32.
+extern "C" void b200TestGetCrossKV(float* out_ck, float* out_cv, int w) {
+    State& s = S();
+    if (!s.ckv || w < 0 || w >= s.ckv_cap) { record_error("b200TestGetCrossKV: no crossKV for window %d", w); return; }
+    const size_t n = s.ckv_window_elems();
+    std::vector<bf16> h(n);
+    B200_CHECK(cudaMemcpy(h.data(), s.ckv + w * n, n * sizeof(bf16), cudaMemcpyDeviceToHost));
+    const size_t hs = (size_t)N_AUDIO_CTX * 64;
+    for (int l = 0; l < s.Ld; ++l)
+        for (int hh = 0; hh < s.H; ++hh) {
+            const bf16* k = h.data() + ((size_t)(l * 2) * s.H + hh) * hs;
+            const bf16* v = h.data() + ((size_t)(l * 2 + 1) * s.H + hh) * hs;
+            float* ok = out_ck + ((size_t)l * s.H + hh) * hs;
+            float* ov = out_cv + ((size_t)l * s.H + hh) * hs;
+            for (int t = 0; t < N_AUDIO_CTX; ++t)
+                for (int c = 0; c < 64; ++c) {
+                    ok[(size_t)c * N_AUDIO_CTX + t] = __bfloat162float(k[(size_t)t * 64 + c]);
+                    ov[(size_t)t * 64 + c] = __bfloat162float(v[(size_t)t * 64 + c]);
+                }
+        }
+}
+
+// Logical KV cache rows [0, n_rows) as fp32 (2Ld, bs, n_rows, d), resolved through the slot table.
+extern "C" void b200TestGetKV(float* out, int n_rows) {
+    State& s = S();
+    if (!s.mkv) { record_error("b200TestGetKV: decoder not loaded"); return; }
+    const size_t total = (size_t)2 * s.Ld * s.bs * N_TEXT_CTX * s.d;
+    std::vector<bf16> h(total);
+    std::vector<int> tab((size_t)STEP_MAX_BEAMS * N_TEXT_CTX);
+    B200_CHECK(cudaMemcpy(h.data(), s.mkv, total * sizeof(bf16), cudaMemcpyDeviceToHost));
+    B200_CHECK(cudaMemcpy(tab.data(), s.table, tab.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int m = 0; m < 2 * s.Ld; ++m)
+        for (int b = 0; b < s.bs; ++b)
+            for (int t = 0; t < n_rows; ++t) {
+                const int slot = tab[b * N_TEXT_CTX + t];
+                const bf16* src = h.data() + (((size_t)m * s.bs + slot) * N_TEXT_CTX + t) * s.d;
+                float* dst = out + (((size_t)m * s.bs + b) * n_rows + t) * s.d;
+                for (int c = 0; c < s.d; ++c) dst[c] = __bfloat162float(src[c]);
+            }
+}

@@ -1,0 +1,332 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   warp 0 (1 thread)  : TMA producer   - cp.async.bulk.tensor into a STAGES-deep smem ring
+//   warp 1 (1 thread)  : MMA issuer     - tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16,
+//                                          accumulators in TMEM, double buffered (2 x BLOCK_N columns)
+//   warps 2..5         : epilogue       - tcgen05.ld -> bias / GELU / residual -> global
+//
+// The epilogue of tile i overlaps the main loop of tile i+1 through the tmem_full / tmem_empty
+// mbarrier pair.  Operands are bf16, K-major, 128-byte swizzled (TMA SWIZZLE_128B <-> UMMA
+// LayoutType 2), accumulation is fp32.
+#include "gemm.cuh"
+
+#include <map>
+#include <tuple>
+#include <vector>
+
+namespace b200 {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;
+static constexpr int GEMM_THREADS = 192;
+
+struct GemmKernelArgs {
+    int num_a_maps, kblocks_per_map, num_kb;
+    int rows_per_batch, m_tiles_per_batch, num_m_tiles, num_n_tiles;
+    int N;
+    const float* bias;
+    int gelu;
+    const float* add;
+    int add_rows;
+    long ld_add;
+    void* C;
+    int c_fp32;
+    long ldc;
+    int c_batch_rows, c_row0;
+    int c_split;
+    long c_split_stride;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                    const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
+                    const GemmKernelArgs g) {
+    constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+    constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;            // power of two: 256 or 512
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = g.num_m_tiles * g.num_n_tiles;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapA0);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (threadIdx.x == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        int s = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n_blk = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
+            const int b = m_tile / g.m_tiles_per_batch, t0 = (m_tile % g.m_tiles_per_batch) * BLOCK_M;
+            for (int kb = 0; kb < g.num_kb; ++kb) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                uint8_t* sa = smem + s * STAGE_BYTES;
+                const int mi = kb / g.kblocks_per_map, c0 = (kb % g.kblocks_per_map) * BLOCK_K;
+                const CUtensorMap* am = mi == 0 ? &mapA0 : (mi == 1 ? &mapA1 : &mapA2);
+                tma_load_3d(sa, am, &full_bar[s], c0, t0, b);
+                tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], kb * BLOCK_K, n_blk * BLOCK_N);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (threadIdx.x == 32) {
+        // ------------------------------ MMA issuer ------------------------------
+        constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+        int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tmem_empty[a], aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + a * BLOCK_N;
+            for (int kb = 0; kb < g.num_kb; ++kb) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t da = umma_desc_k128(sa), db = umma_desc_k128(sa + A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / 16; ++k)      // +32 B per K=16 slice inside the swizzle atom
+                    umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(&empty_bar[s]);                 // frees the smem stage when the MMAs retire
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            umma_commit(&tmem_full[a]);                     // accumulator ready for the epilogue
+            if (++a == 2) { a = 0; aph ^= 1; }
+        }
+    } else if (warp >= 2) {
+        // ------------------------------ epilogue ------------------------------
+        const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
+        int a = 0; uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n_blk = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
+            const int b = m_tile / g.m_tiles_per_batch, t0 = (m_tile % g.m_tiles_per_batch) * BLOCK_M;
+            const int t = t0 + quad * 32 + lane;
+            const bool row_ok = t < g.rows_per_batch;
+            const long c_row = (long)b * g.c_batch_rows + g.c_row0 + t;
+            const long m_flat = (long)b * g.rows_per_batch + t;
+            const float* add_row = g.add ? g.add + (m_flat % g.add_rows) * g.ld_add : nullptr;
+            mbar_wait(&tmem_full[a], aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + a * BLOCK_N + c * 32, r);
+                tmem_ld_wait();
+                const int n0 = n_blk * BLOCK_N + c * 32;
+                if (!row_ok || n0 >= g.N) continue;
+                float v[32];
+                const bool full = n0 + 32 <= g.N;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float x = __uint_as_float(r[i]);
+                    if (g.bias && (full || n0 + i < g.N)) x += __ldg(g.bias + n0 + i);
+                    if (g.gelu) x = gelu_erf(x);
+                    v[i] = x;
+                }
+                if (add_row) {
+                    if (full) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float4 q = *reinterpret_cast<const float4*>(add_row + n0 + i);
+                            v[i] += q.x; v[i + 1] += q.y; v[i + 2] += q.z; v[i + 3] += q.w;
+                        }
+                    } else {
+                        for (int i = 0; i < 32 && n0 + i < g.N; ++i) v[i] += add_row[n0 + i];
+                    }
+                }
+                // split mode: 64-column groups (heads) are c_split_stride elements apart
+                const long col_off = g.c_split ? (long)(n0 >> 6) * g.c_split_stride + (n0 & 63) : (long)n0;
+                if (g.c_fp32) {
+                    float* out = reinterpret_cast<float*>(g.C) + c_row * g.ldc + col_off;
+                    if (full) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4*>(out + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+                        for (int i = 0; i < 32 && n0 + i < g.N; ++i) out[i] = v[i];
+                    }
+                } else {
+                    bf16* out = reinterpret_cast<bf16*>(g.C) + c_row * g.ldc + col_off;
+                    if (full) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            uint4 q;
+                            q.x = pack_bf16(v[i], v[i + 1]); q.y = pack_bf16(v[i + 2], v[i + 3]);
+                            q.z = pack_bf16(v[i + 4], v[i + 5]); q.w = pack_bf16(v[i + 6], v[i + 7]);
+                            *reinterpret_cast<uint4*>(out + i) = q;
+                        }
+                    } else {
+                        for (int i = 0; i < 32 && n0 + i < g.N; ++i) out[i] = __float2bfloat16(v[i]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[a]);
+            if (++a == 2) { a = 0; aph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+            record_error("cuTensorMapEncodeTiled entry point unavailable");
+            return nullptr;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// bf16 tensor map with a (64 x box_rows [x 1]) box and 128-byte swizzle, zero OOB fill.
+static bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[3] = {dims[0], dims[1], rank == 3 ? dims[2] : 1};
+    cuuint64_t gstr[2] = {strides_bytes[0], rank == 3 ? strides_bytes[1] : 0};
+    cuuint32_t box[3] = {BLOCK_K, box_rows, 1};
+    cuuint32_t est[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, box, est,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        record_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu strides %llu %llu base %p", (int)r, rank,
+                     (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2],
+                     (unsigned long long)gstr[0], (unsigned long long)gstr[1], base);
+        return false;
+    }
+    return true;
+}
+
+typedef std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint32_t> MapKey;
+static std::map<MapKey, CUtensorMap> g_map_cache;
+
+static const CUtensorMap* cached_map(const void* base, int rank, const uint64_t* dims, const uint64_t* str, uint32_t box_rows) {
+    MapKey key(base, rank, dims[0], dims[1], rank == 3 ? dims[2] : 1, str[0], rank == 3 ? str[1] : 0, box_rows);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) return &it->second;
+    CUtensorMap m;
+    if (!make_map(&m, base, rank, dims, str, box_rows)) return nullptr;
+    return &g_map_cache.emplace(key, m).first->second;
+}
+
+void gemm_clear_map_cache() { g_map_cache.clear(); }
+
+static int g_num_sms = 0;
+
+template <int BLOCK_N, int STAGES>
+static void launch(const GemmParams& p, cudaStream_t stream) {
+    const CUtensorMap* am[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < p.num_a_maps; ++i) {
+        uint64_t dims[3] = {(uint64_t)p.a_inner, (uint64_t)p.rows_per_batch, (uint64_t)p.batch};
+        uint64_t str[2] = {(uint64_t)p.a_row_stride * 2, (uint64_t)p.a_batch_stride * 2};
+        am[i] = cached_map(p.A[i], 3, dims, str, BLOCK_M);
+        if (!am[i]) return;
+    }
+    for (int i = p.num_a_maps; i < 3; ++i) am[i] = am[0];
+    uint64_t bdims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t bstr[1] = {(uint64_t)p.ldb * 2};
+    const CUtensorMap* bm = cached_map(p.B, 2, bdims, bstr, BLOCK_N);
+    if (!bm) return;
+
+    GemmKernelArgs g;
+    g.num_a_maps = p.num_a_maps; g.kblocks_per_map = p.kblocks_per_map; g.num_kb = p.K / BLOCK_K;
+    g.rows_per_batch = p.rows_per_batch; g.m_tiles_per_batch = cdiv(p.rows_per_batch, BLOCK_M);
+    g.num_m_tiles = g.m_tiles_per_batch * p.batch; g.num_n_tiles = cdiv(p.N, BLOCK_N);
+    g.N = p.N; g.bias = p.bias; g.gelu = p.gelu; g.add = p.add; g.add_rows = p.add_rows > 0 ? p.add_rows : 1;
+    g.ld_add = p.ld_add; g.C = p.C; g.c_fp32 = p.c_fp32; g.ldc = p.ldc; g.c_batch_rows = p.c_batch_rows; g.c_row0 = p.c_row0;
+    g.c_split = p.c_split; g.c_split_stride = p.c_split_stride;
+
+    constexpr size_t smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int tiles = g.num_m_tiles * g.num_n_tiles;
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    gemm_tcgen05_kernel<BLOCK_N, STAGES><<<grid, GEMM_THREADS, smem, stream>>>(*am[0], *am[1], *am[2], *bm, g);
+    B200_LAUNCH_CHECK();
+}
+
+void gemm_tcgen05(const GemmParams& p, cudaStream_t stream) {
+    if (p.K % BLOCK_K != 0) { record_error("gemm_tcgen05: K=%d is not a multiple of 64", p.K); return; }
+    // 128x256 tiles keep the smem operand read rate under the 128 B/clk port limit; fall back to
+    // 128x128 when the problem would not give every SM a tile.
+    const long tiles256 = (long)p.batch * cdiv(p.rows_per_batch, BLOCK_M) * cdiv(p.N, 256);
+    if (tiles256 >= 120 && p.N >= 256) launch<256, 4>(p, stream);
+    else launch<128, 6>(p, stream);
+}
+
+GemmParams gemm_plain(const bf16* A, const bf16* B, void* C, int M, int N, int K) {
+    GemmParams p{};
+    p.A[0] = A; p.num_a_maps = 1; p.kblocks_per_map = K / BLOCK_K; p.a_inner = K; p.a_row_stride = K;
+    p.a_batch_stride = (long)M * K; p.rows_per_batch = M; p.batch = 1;
+    p.B = B; p.ldb = K; p.N = N; p.K = K;
+    p.C = C; p.ldc = N; p.c_batch_rows = 0; p.c_row0 = 0; p.add_rows = 1;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SIMT checker: one thread per output element, fp32 accumulation in K order.  Tests only.
+// ---------------------------------------------------------------------------------------------------
+__global__ void gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B, const float* __restrict__ bias,
+                                 void* C, int M, int N, int K, int c_fp32, int gelu) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+    if (n >= N || m >= M) return;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc += __bfloat162float(A[(long)m * K + k]) * __bfloat162float(B[(long)n * K + k]);
+    if (bias) acc += bias[n];
+    if (gelu) acc = gelu_erf(acc);
+    if (c_fp32) reinterpret_cast<float*>(C)[(long)m * N + n] = acc;
+    else reinterpret_cast<bf16*>(C)[(long)m * N + n] = __float2bfloat16(acc);
+}
+
+void gemm_simt(const bf16* A, const bf16* B, const float* bias, void* C, int M, int N, int K, int c_fp32, int gelu,
+               cudaStream_t stream) {
+    dim3 grid(cdiv(N, 128), M);
+    gemm_simt_kernel<<<grid, 128, 0, stream>>>(A, B, bias, C, M, N, K, c_fp32, gelu);
+    B200_LAUNCH_CHECK();
+}
+
+}  // namespace b200
