@@ -106,13 +106,15 @@ void b200SelectWindow(int w);
 /* Device-resident DecodingTask.run at temperature 0 for the current window
  * (whisper/decoding.py:707-816): prefill of `n_initial` tokens, then up to `sample_len` steps of
  * decoder1 + logit filters + greedy/beam update, all on the GPU, one host sync at the end.
- * beam_size==1 -> GreedyDecoder (:299-325), else BeamSearchDecoder (:328-431), patience 1.
+ * beam_size <= 0 -> GreedyDecoder (:299-325, the reference's beam_size=None), else BeamSearchDecoder
+ * (:328-431) with that many beams (<= the beam_size given to loadDecoder256), patience 1.
  * Outputs (HOST):
  *   out_tokens     (n_cand, 449) int32  candidate sequences incl. initial tokens, EOT padded
  *   out_lengths    (n_cand)      int32  tokens before the first EOT after sample_begin
  *   out_sum_logprobs (n_cand)    float
  *   out_no_speech  (1)           float  softmax(logits[sot_index])[no_speech]
- * n_cand = beam_size.  Returns the number of decoder1 steps executed. */
+ * n_cand = max(beam_size, 1); unused rows have length -1.  Ranking (MaximumLikelihoodRanker, :217-240) is
+ * left to the caller.  Returns the number of sampling steps executed (the prefill step included). */
 int b200DecodeWindow(const int* initial_tokens, int n_initial, int beam_size, int sample_len,
                      int without_timestamps, int max_initial_timestamp_index,
                      int* out_tokens, int* out_lengths, float* out_sum_logprobs, float* out_no_speech);
@@ -132,10 +134,13 @@ void medianFilter(const float* x, float* y, long rows, int len, int width);
 int dtw(const float* x, int N, int M, int* out_i, int* out_j);
 /* whisper/timing.py:194-204 on the device for the CHW of the last decoder256Predict / alignment
  * pass: softmax over frames[:num_frames/2] -> z-score over tokens -> median(width) -> mean over
- * heads -> rows [n_skip, n_tokens-1) -> DTW.  Returns path length; out_matrix (optional, HOST,
- * (n_tokens-1-n_skip, num_frames/2)). */
+ * heads -> rows [n_skip, n_tokens-1) -> DTW(-matrix).  tokens = [*sot_sequence, no_timestamps, *text, eot]
+ * (timing.py:176-183), n_skip = len(sot_sequence).  Runs one decoder256 pass for the current window (it
+ * overwrites KV slot 0).  Returns the path length (out_i/out_j capacity n_tokens + num_frames/2);
+ * optional HOST outputs: out_matrix (n_tokens-1-n_skip, num_frames/2) and out_text_token_probs
+ * (n_tokens-n_skip-2): softmax over [:eot] at each text token (timing.py:187-190). */
 int b200AlignTokens(const int* tokens, int n_tokens, int n_skip, int num_frames, int medfilt_width,
-                    int* out_i, int* out_j, float* out_matrix, float* out_token_logits_at_next);
+                    int* out_i, int* out_j, float* out_matrix, float* out_text_token_probs);
 
 /* Per-stage device time (ms, CUDA events) accumulated since the last reset - the analogue of
  * whisper/coreml.py:9-13,247-263.  stages: 0 mel, 1 encoder, 2 crossKV, 3 decoder256, 4 decoder1,
@@ -148,6 +153,11 @@ long b200KernelLaunchCount();
  * tcgen05 GEMM and through the SIMT checker; device pointers, bf16 inputs. */
 void b200TestGemm(const void* dA, const void* dB, const float* dBias, void* dC, int M, int N, int K,
                   int out_fp32, int gelu, int use_simt);
+/* State read-back as fp32 HOST arrays in the reference's layouts: Xa (1500, d) of window w;
+ * CK (Ld,H,64,1500) / CV (Ld,H,1500,64) of window w; logical KV cache rows (2Ld, bs, n_rows, d). */
+void b200TestGetXa(float* out, int w);
+void b200TestGetCrossKV(float* out_ck, float* out_cv, int w);
+void b200TestGetKV(float* out, int n_rows);
 
 #if __cplusplus
 }

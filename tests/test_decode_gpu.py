@@ -1,0 +1,88 @@
+"""Device-resident decode loop (b200DecodeWindow) and word-timestamp alignment against the oracle and the
+reference goldens.  BASELINE.json: greedy/beam token sequences >= 99% identical; DTW paths bit-exact given
+the same cost matrix."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import audio as oa, decoding as od, model as om, synth, timing as ot
+from tests._util import exported, golden, rel
+
+pytestmark = pytest.mark.gpu
+
+CASES = {  # name -> (dims name, seed, logit_scale, sample_len, golden tag)
+    "nano": ("nano", 0, 1.0, 24, "nano"),
+    "nano_soft": ("nano", 1, 0.03, 40, "nano_soft"),
+    "tiny": ("tiny", 0, 1.0, 24, "tiny"),
+}
+
+
+def _mel(dims):
+    audio = synth.noise_audio(1, 480000)
+    return oa.log_mel_spectrogram(audio, dims.n_mels, padding=480000)[:, :3000].contiguous()
+
+
+def _agreement(a, b):
+    n = max(len(a), len(b), 1)
+    return sum(x == y for x, y in zip(a, b)) / n
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request):
+    from whisper_b200.model import ModelDimensions, WhisperB200
+    name, seed, scale, sample_len, tag = CASES[request.param]
+    dims, ckpt, folder = exported(name, seed, scale)
+    m = WhisperB200(ModelDimensions(**dims.as_dict()), folder).load()
+    orc = om.OracleModel(dims, ckpt)
+    mel = _mel(dims)
+    m.encode_windows(mel.cuda(), [0])
+    yield m, orc, dims, mel, sample_len, golden(tag)
+    m.close()
+
+
+@pytest.mark.parametrize("beam", [None, 5])
+def test_tokens_match_oracle_and_reference(case, beam):
+    from whisper_b200.decoding import DecodingOptions, decode
+    m, orc, dims, mel, sample_len, g = case
+    sp = od.Specials.load(dims.n_vocab)
+    want = od.decode_window(orc, mel, sp, od.Options(sample_len=sample_len, beam_size=beam))
+    got = decode(m, DecodingOptions(sample_len=sample_len, beam_size=beam), window=0)
+    tag = "beam5" if beam else "greedy"
+    ref_tokens = g[f"{tag}_tokens"].tolist()
+    assert _agreement(got.tokens, want.tokens) >= 0.99, (got.tokens, want.tokens)
+    assert _agreement(got.tokens, ref_tokens) >= 0.99, (got.tokens, ref_tokens)
+    assert got.steps == want.steps
+    assert abs(got.avg_logprob - want.avg_logprob) <= 2e-2 * max(1.0, abs(want.avg_logprob))
+    assert abs(got.no_speech_prob - want.no_speech_prob) <= 2e-2
+
+
+def test_without_timestamps_and_length_penalty(case):
+    from whisper_b200.decoding import DecodingOptions, decode
+    m, orc, dims, mel, sample_len, g = case
+    sp = od.Specials.load(dims.n_vocab)
+    want = od.decode_window(orc, mel, sp, od.Options(sample_len=12, beam_size=5, without_timestamps=True, length_penalty=1.0))
+    got = decode(m, DecodingOptions(sample_len=12, beam_size=5, without_timestamps=True, length_penalty=1.0), window=0)
+    assert _agreement(got.tokens, want.tokens) >= 0.99, (got.tokens, want.tokens)
+
+
+def test_alignment(case):
+    from whisper_b200.timing import align_tokens
+    m, orc, dims, mel, sample_len, g = case
+    sp = od.Specials.load(dims.n_vocab)
+    tokens = g["align_tokens"].tolist()                      # [*sot_sequence, no_timestamps, *text, eot]
+    n_skip = len(sp.sot_sequence)
+    text = tokens[n_skip + 1:-1]
+    al = align_tokens(sp.sot_sequence, sp.no_timestamps, sp.eot, text, 3000)
+    # matrix close to the oracle's and to the reference golden (sub-sampled every 10 frames)
+    orc.reset(); orc.xa = orc.encode(mel)
+    _, chw = orc.logits(torch.tensor([tokens]))
+    orc.reset()
+    mat = ot.alignment_matrix(chw, 3000, n_skip)
+    assert al.matrix.shape == tuple(mat.shape)
+    assert rel(al.matrix, mat) < 5e-2, rel(al.matrix, mat)
+    assert rel(al.matrix[:, ::10], g["align_matrix"]) < 5e-2
+    # DTW: bit-exact given the same cost matrix
+    oi, oj = ot.dtw(-al.matrix)
+    assert np.array_equal(al.text_indices, oi) and np.array_equal(al.time_indices, oj)
+    assert len(al.text_token_probs) == len(text) and np.all(al.text_token_probs >= 0) and np.all(al.text_token_probs <= 1)
+    assert len(al.jump_times) == len(text) + 1              # one start time per matrix row (no_timestamps row + text rows)

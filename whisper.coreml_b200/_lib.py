@@ -34,6 +34,17 @@ SIGNATURES = {
     "b200SetDevice": (None, [c_int]),
     "b200SetAlignmentHeads": (None, [i32p, c_int]),
     "b200SelectWindow": (None, [c_int]),
+    "b200SetDecodeSpec": (None, [c_int, c_int, c_int, c_int, c_int, i32p, c_int, i32p, c_int]),
+    "logMelSpectrogram": (c_long, [f32p, c_long, c_long, c_int, f32p]),
+    "logMelSpectrogramDev": (c_long, [c_void_p, c_long, c_long, c_int, c_void_p]),
+    "encoderPredictWindows": (None, [c_void_p, c_long, i32p, c_int]),
+    "crossKVPredictWindows": (None, [c_int]),
+    "b200DecodeWindow": (c_int, [i32p, c_int, c_int, c_int, c_int, c_int, i32p, i32p, f32p, f32p]),
+    "decoder1StepFused": (None, [i32p, c_int, c_int, c_int, c_int, c_int, f32p, i32p]),
+    "medianFilter": (None, [f32p, f32p, c_long, c_int, c_int]),
+    "dtw": (c_int, [f32p, c_int, c_int, i32p, i32p]),
+    "b200AlignTokens": (c_int, [i32p, c_int, c_int, c_int, c_int, i32p, i32p, f32p, f32p]),
+    "b200GetStageTimes": (None, [f32p, c_int]),
     # test hooks
     "b200TestGemm": (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
     "b200TestGetXa": (None, [f32p, c_int]),

@@ -15,7 +15,11 @@ void gemm_clear_map_cache();
 
 State& S() { static State s; return s; }
 
-static void use_device() { B200_CHECK(cudaSetDevice(S().device)); }
+void use_device() {
+    State& s = S();
+    B200_CHECK(cudaSetDevice(s.device));
+    if (!s.stream) B200_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+}
 
 // =================================================================================================
 // encoder (whisper/encoder.py:103-136)
@@ -123,6 +127,17 @@ void run_cross_kv(int W) {
 // =================================================================================================
 // decoder256 prefill (whisper/decoder.py:261-329 with qk_mask.shape[0] == 256; coreml.mm:279-327)
 // =================================================================================================
+struct PermuteArgs { int src[STEP_MAX_BEAMS]; };
+__global__ void permute_table_kernel(int* table, PermuteArgs pa, int bs, int n) {
+    __shared__ int stage[STEP_MAX_BEAMS * N_TEXT_CTX];
+    for (int i = threadIdx.x; i < bs * N_TEXT_CTX; i += blockDim.x) stage[i] = table[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < bs * n; i += blockDim.x) {
+        const int b = i / n, p = i % n;
+        table[b * N_TEXT_CTX + p] = stage[pa.src[b] * N_TEXT_CTX + p];
+    }
+}
+
 __global__ void fill_table_kernel(int* table, int beam, int n, int value) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) table[beam * N_TEXT_CTX + i] = value;
@@ -175,64 +190,62 @@ void run_prefill(int beam_idx, bool want_chw) {
     layernorm(s.px, s.ln_w, s.ln_b, 1e-5f, nullptr, s.pout, M, d, st);  // decoder.py:316
     fill_table_kernel<<<1, 256, 0, st>>>(s.table, beam_idx, M, beam_idx);
     B200_LAUNCH_CHECK();
-    for (int i = 0; i < M; ++i) s.h_table[beam_idx * N_TEXT_CTX + i] = beam_idx;
 }
 
 // =================================================================================================
 // decoder1 step (whisper/decoder.py:241-257, 261-327; coreml.mm:404-444)
 // =================================================================================================
-void run_step(int nb, int t, const float* d_mask, bool want_logits) {
+void run_step(int nb, int t, const float* d_mask, bool want_logits, const int* d_t, const int* d_skip) {
     State& s = S();
     const int d = s.d;
     cudaStream_t st = s.stream;
     for (int l = 0; l < s.Ld; ++l) {
         const DecLayer& L = s.dec_layers[l];
         StepGemv g{};
-        g.nb = nb; g.eps = 1e-5f;
+        g.nb = nb; g.eps = 1e-5f; g.d_skip = d_skip;
         // LN + fused q|k|v
         g.w_frag = L.qkv.frag; g.bias = L.qkv.b; g.N = 3 * d; g.K = d; g.x_f32 = s.sx; g.ld_x = d;
         g.ln_g = L.attn_ln_w; g.ln_b = L.attn_ln_b; g.out_f32 = s.sqkv; g.ld_out = 3L * d;
         step_gemv(g, st);
         StepSelfAttn a{};
         a.qkv = s.sqkv; a.cache_k = s.mk_ptr(l); a.cache_v = s.mv_ptr(l); a.table = s.table; a.mask = d_mask;
-        a.text_offset = t; a.nb = nb; a.n_head = s.H; a.d = d; a.out = s.satt;
+        a.text_offset = t; a.d_text_offset = d_t; a.d_skip = d_skip; a.nb = nb; a.n_head = s.H; a.d = d; a.out = s.satt;
         step_self_attn(a, st);
         // out projection + residual (in place)
-        g = StepGemv{}; g.nb = nb;
+        g = StepGemv{}; g.nb = nb; g.d_skip = d_skip;
         g.w_frag = L.attn_out.frag; g.bias = L.attn_out.b; g.N = d; g.K = d; g.x_bf16 = s.satt; g.ld_x = d;
         g.residual = s.sx; g.ld_res = d; g.out_f32 = s.sx; g.ld_out = d;
         step_gemv(g, st);
         // LN + cross query
-        g = StepGemv{}; g.nb = nb; g.eps = 1e-5f;
+        g = StepGemv{}; g.nb = nb; g.d_skip = d_skip; g.eps = 1e-5f;
         g.w_frag = L.cross_q.frag; g.bias = L.cross_q.b; g.N = d; g.K = d; g.x_f32 = s.sx; g.ld_x = d;
         g.ln_g = L.cross_ln_w; g.ln_b = L.cross_ln_b; g.out_f32 = s.sq; g.ld_out = d;
         step_gemv(g, st);
         StepCrossAttn c{};
         c.q = s.sq; c.ck = s.ck_ptr(s.cur_window, l); c.cv = s.cv_ptr(s.cur_window, l); c.nb = nb; c.n_head = s.H;
-        c.d = d; c.n_keys = N_AUDIO_CTX; c.part = s.spart; c.counters = s.scounters; c.out = s.satt;
+        c.d = d; c.n_keys = N_AUDIO_CTX; c.part = s.spart; c.counters = s.scounters; c.out = s.satt; c.d_skip = d_skip;
         step_cross_attn(c, st);
-        g = StepGemv{}; g.nb = nb;
+        g = StepGemv{}; g.nb = nb; g.d_skip = d_skip;
         g.w_frag = L.cross_out.frag; g.bias = L.cross_out.b; g.N = d; g.K = d; g.x_bf16 = s.satt; g.ld_x = d;
         g.residual = s.sx; g.ld_res = d; g.out_f32 = s.sx; g.ld_out = d;
         step_gemv(g, st);
         // LN + MLP
-        g = StepGemv{}; g.nb = nb; g.eps = 1e-5f;
+        g = StepGemv{}; g.nb = nb; g.d_skip = d_skip; g.eps = 1e-5f;
         g.w_frag = L.mlp1.frag; g.bias = L.mlp1.b; g.N = 4 * d; g.K = d; g.x_f32 = s.sx; g.ld_x = d;
         g.ln_g = L.mlp_ln_w; g.ln_b = L.mlp_ln_b; g.gelu = 1; g.out_bf16 = s.shid; g.ld_out = 4L * d;
         step_gemv(g, st);
-        g = StepGemv{}; g.nb = nb;
+        g = StepGemv{}; g.nb = nb; g.d_skip = d_skip;
         g.w_frag = L.mlp2.frag; g.bias = L.mlp2.b; g.N = d; g.K = 4 * d; g.x_bf16 = s.shid; g.ld_x = 4L * d;
         g.residual = s.sx; g.ld_res = d; g.out_f32 = s.sx; g.ld_out = d;
         step_gemv(g, st);
     }
     if (want_logits) {                                                  // final LN + tied vocabulary projection
         StepGemv g{};
-        g.nb = nb; g.eps = 1e-5f;
+        g.nb = nb; g.eps = 1e-5f; g.d_skip = d_skip;
         g.w_frag = s.tok_emb_frag; g.N = s.V; g.K = d; g.x_f32 = s.sx; g.ld_x = d; g.ln_g = s.ln_w; g.ln_b = s.ln_b;
         g.out_f32 = s.slogits; g.ld_out = s.V;
         step_gemv(g, st);
     }
-    for (int b = 0; b < nb; ++b) s.h_table[b * N_TEXT_CTX + t] = b;
 }
 
 // =================================================================================================
@@ -395,7 +408,6 @@ void loadDecoder256(const char* modelPath, int n_layer, int n_state, int n_head,
     bool ok = true;
     ok &= dev_alloc(&s.mkv, (size_t)2 * s.Ld * s.bs * N_TEXT_CTX * d, true);    // coreml.mm:231-233
     ok &= dev_alloc(&s.table, (size_t)STEP_MAX_BEAMS * N_TEXT_CTX, true);
-    s.h_table.assign((size_t)STEP_MAX_BEAMS * N_TEXT_CTX, 0);
     ok &= dev_alloc(&s.px, M * d); ok &= dev_alloc(&s.pout, M * d); ok &= dev_alloc(&s.pmask, M * M);
     ok &= dev_alloc(&s.pchw, (size_t)(s.n_align > 0 ? s.n_align : 1) * M * N_AUDIO_CTX);
     ok &= dev_alloc(&s.py, M * d); ok &= dev_alloc(&s.pqkv, M * 3 * d); ok &= dev_alloc(&s.patt, M * d);
@@ -471,13 +483,15 @@ void rearrange_mkv(int* indices, int text_offset) {
     if (!s.dec256_loaded) { record_error("rearrange_mkv: decoder not loaded"); return; }
     if (text_offset < 0 || text_offset > N_TEXT_CTX) { record_error("rearrange_mkv: text_offset %d", text_offset); return; }
     use_device();
-    std::vector<int> old(s.h_table);
+    int h_idx[STEP_MAX_BEAMS];
     for (int b = 0; b < s.bs; ++b) {
-        const int src = indices[b];
-        if (src < 0 || src >= s.bs) { record_error("rearrange_mkv: index %d outside [0, %d)", src, s.bs); return; }
-        memcpy(&s.h_table[b * N_TEXT_CTX], &old[src * N_TEXT_CTX], (size_t)text_offset * sizeof(int));
+        h_idx[b] = indices[b];
+        if (h_idx[b] < 0 || h_idx[b] >= s.bs) { record_error("rearrange_mkv: index %d outside [0, %d)", h_idx[b], s.bs); return; }
     }
-    B200_CHECK(cudaMemcpyAsync(s.table, s.h_table.data(), (size_t)s.bs * N_TEXT_CTX * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+    PermuteArgs pa;
+    for (int b = 0; b < STEP_MAX_BEAMS; ++b) pa.src[b] = b < s.bs ? h_idx[b] : b;
+    permute_table_kernel<<<1, 256, 0, s.stream>>>(s.table, pa, s.bs, text_offset);
+    B200_LAUNCH_CHECK();
     B200_CHECK(cudaStreamSynchronize(s.stream));
 }
 
@@ -490,7 +504,7 @@ void decoder1Predict(float* x, float* qk_mask, int text_offset, float* out_x) {
     const int nb = s.bs;
     B200_CHECK(cudaMemcpyAsync(s.sx, x, nb * d * sizeof(float), cudaMemcpyHostToDevice, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.smask, qk_mask, (size_t)(nb == 1 ? 450 : 449) * sizeof(float), cudaMemcpyHostToDevice, s.stream));
-    run_step(nb, text_offset, s.smask, true);
+    run_step(nb, text_offset, s.smask, true, nullptr, nullptr);
     B200_CHECK(cudaMemcpyAsync(out_x, s.slogits, (size_t)nb * s.V * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     B200_CHECK(cudaStreamSynchronize(s.stream));
 }

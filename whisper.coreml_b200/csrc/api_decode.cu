@@ -1,0 +1,329 @@
+// C ABI Part 2: batched windows and the device-resident decode loop.
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "decoder_step.cuh"
+#include "ops.cuh"
+#include "sampling.cuh"
+#include "gemm.cuh"
+#include "state.cuh"
+#include "timing.cuh"
+#include "whisper_b200.h"
+
+namespace b200 {
+
+struct DecodeCtx {
+    DecodeSpec spec;
+    std::vector<uint8_t> h_suppress;
+    uint8_t* d_suppress = nullptr;
+    DecodeState* st = nullptr;          // device
+    int* tokens = nullptr;              // [8][449]
+    int* fin_tokens = nullptr;          // [8][449]
+    float* cand_lp = nullptr; int* cand_tok = nullptr;   // [8][9]
+    float* ns_logits = nullptr;         // [V] logits at the sot position
+    int* pin_done = nullptr;            // pinned host
+    bool ready = false;
+};
+static DecodeCtx g_dc;
+
+static bool ensure_decode_ctx() {
+    DecodeCtx& c = g_dc;
+    State& s = S();
+    if (c.spec.n_vocab != s.V || c.spec.eot < 0) { record_error("decode: call b200SetDecodeSpec (n_vocab %d) first", s.V); return false; }
+    if (c.ready) return true;
+    bool ok = true;
+    ok &= dev_alloc(&c.st, 1, true);
+    ok &= dev_alloc(&c.tokens, (size_t)DEC_MAX_BEAMS * DEC_TOK_LD, true);
+    ok &= dev_alloc(&c.fin_tokens, (size_t)DEC_MAX_BEAMS * DEC_TOK_LD, true);
+    ok &= dev_alloc(&c.cand_lp, (size_t)DEC_MAX_BEAMS * (DEC_MAX_BEAMS + 1));
+    ok &= dev_alloc(&c.cand_tok, (size_t)DEC_MAX_BEAMS * (DEC_MAX_BEAMS + 1));
+    ok &= dev_alloc(&c.ns_logits, (size_t)s.V);
+    if (!c.pin_done) ok &= cudaMallocHost((void**)&c.pin_done, 64) == cudaSuccess;
+    c.ready = ok;
+    return ok;
+}
+
+// x256[r] = tok_emb[tok[r]] + pos_emb[r] for r < n, zero rows after (decoder.py:202,214); mask = causal with
+// columns >= n masked (decoder.py:212-213)
+__global__ void prefill_inputs_kernel(const bf16* __restrict__ tok_emb, const float* __restrict__ pos_emb,
+                                      const int* __restrict__ tokens, int n, int d, float* __restrict__ x, float* __restrict__ mask) {
+    const int r = blockIdx.x;
+    const int tok = r < n ? tokens[r] : 0;
+    for (int c = threadIdx.x; c < d; c += blockDim.x)
+        x[(long)r * d + c] = r < n ? __bfloat162float(tok_emb[(long)tok * d + c]) + pos_emb[(long)r * d + c] : 0.f;
+    for (int c = threadIdx.x; c < PREFILL_CTX; c += blockDim.x)
+        mask[r * PREFILL_CTX + c] = (c <= r && c < n) ? 0.f : -INFINITY;
+}
+__global__ void init_tokens_kernel(int* tokens, const int* initial, int n, int nb, int eot, int* table) {
+    for (int i = threadIdx.x; i < nb * DEC_TOK_LD; i += blockDim.x) {
+        const int p = i % DEC_TOK_LD;
+        tokens[i] = p < n ? initial[p] : eot;
+    }
+    for (int i = threadIdx.x; i < nb * N_TEXT_CTX; i += blockDim.x) table[i] = 0;     // every beam reads the prefill from slot 0
+}
+
+struct AlignCtx {
+    float *tmp = nullptr, *mat = nullptr, *neg = nullptr, *logits = nullptr, *probs = nullptr;
+    bf16* rows = nullptr;
+    int *path = nullptr, *targets = nullptr, *d_tok = nullptr;
+    uint8_t* scratch = nullptr;
+    size_t tmp_cap = 0;
+    bool ready = false;
+};
+static AlignCtx g_al;
+
+__global__ void negate_kernel(const float* __restrict__ in, float* __restrict__ out, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = -in[i];
+}
+__global__ void token_prob_kernel(const float* __restrict__ logits, long ld, int eot, const int* __restrict__ targets,
+                                  float* __restrict__ out);
+
+static void launch_sampling(int nb, int k) {
+    State& s = S();
+    DecodeCtx& c = g_dc;
+    SampleArgs sa{};
+    sa.logits = s.slogits; sa.ld_logits = s.V; sa.tokens = c.tokens; sa.st = c.st; sa.spec = c.spec; sa.nb = nb; sa.k = k;
+    sa.cand_lp = c.cand_lp; sa.cand_tok = c.cand_tok;
+    sample_topk(sa, s.stream);
+    BeamUpdateArgs ba{};
+    ba.cand_lp = c.cand_lp; ba.cand_tok = c.cand_tok; ba.nb = nb; ba.k = k; ba.tokens = c.tokens; ba.table = s.table;
+    ba.fin_tokens = c.fin_tokens; ba.st = c.st; ba.eot = c.spec.eot; ba.n_text_ctx = N_TEXT_CTX;
+    beam_update(ba, s.stream);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+void b200SetDecodeSpec(int sot, int eot, int no_timestamps, int timestamp_begin, int no_speech, const int* suppress,
+                       int n_suppress, const int* blank, int n_blank) {
+    State& s = S();
+    DecodeCtx& c = g_dc;
+    if (!s.V) { record_error("b200SetDecodeSpec: load the decoder first (n_vocab unknown)"); return; }
+    use_device();
+    c.spec.sot = sot; c.spec.eot = eot; c.spec.no_timestamps = no_timestamps; c.spec.timestamp_begin = timestamp_begin;
+    c.spec.no_speech = no_speech; c.spec.n_vocab = s.V;
+    for (int i = 0; i < 4; ++i) c.spec.blank[i] = i < n_blank ? blank[i] : -1;
+    c.h_suppress.assign((size_t)s.V, 0);
+    for (int i = 0; i < n_suppress; ++i)
+        if (suppress[i] >= 0 && suppress[i] < s.V) c.h_suppress[suppress[i]] = 1;
+    if (!dev_alloc(&c.d_suppress, (size_t)s.V)) return;
+    B200_CHECK(cudaMemcpy(c.d_suppress, c.h_suppress.data(), (size_t)s.V, cudaMemcpyHostToDevice));
+    c.spec.d_suppress = c.d_suppress;
+}
+
+void encoderPredictWindows(const float* d_mel, long total_frames, const int* seeks, int n_windows) {
+    State& s = S();
+    if (!s.enc_loaded) { record_error("encoderPredictWindows: encoder not loaded"); return; }
+    if (n_windows < 1) return;
+    use_device();
+    B200_CHECK(cudaStreamSynchronize(cudaStreamLegacy));                // d_mel may have been produced on the caller's stream
+    if (!ensure_encoder_capacity(n_windows)) return;
+    B200_CHECK(cudaMemcpyAsync(s.d_seeks, seeks, (size_t)n_windows * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+    {
+        StageTimer t(ST_ENCODER);
+        run_encoder(d_mel, total_frames, n_windows);
+    }
+    s.cur_window = 0;
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+void crossKVPredictWindows(int n_windows) {
+    State& s = S();
+    if (!s.ckv_loaded || !s.enc_loaded) { record_error("crossKVPredictWindows: encoder / crossKV not loaded"); return; }
+    if (n_windows < 1 || n_windows > s.n_windows) { record_error("crossKVPredictWindows: %d windows requested, %d encoded", n_windows, s.n_windows); return; }
+    use_device();
+    {
+        StageTimer t(ST_CROSSKV);
+        run_cross_kv(n_windows);
+    }
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+int b200DecodeWindow(const int* initial_tokens, int n_initial, int beam_size, int sample_len, int without_timestamps,
+                     int max_initial_timestamp_index, int* out_tokens, int* out_lengths, float* out_sum_logprobs,
+                     float* out_no_speech) {
+    State& s = S();
+    DecodeCtx& c = g_dc;
+    if (!s.dec1_loaded || !s.dec256_loaded || !s.ckv_loaded) { record_error("b200DecodeWindow: decoder256 / decoder1 / crossKV not loaded"); return 0; }
+    const int nb = beam_size > 0 ? beam_size : 1;
+    if (nb > s.bs) { record_error("b200DecodeWindow: %d beams but loadDecoder256 reserved %d cache slots", nb, s.bs); return 0; }
+    if (n_initial < 1 || n_initial > PREFILL_CTX) { record_error("b200DecodeWindow: n_initial %d outside [1, 256]", n_initial); return 0; }
+    if (sample_len < 1) return 0;
+    use_device();
+    if (!ensure_decode_ctx()) return 0;
+    cudaStream_t st = s.stream;
+    const int d = s.d, k = beam_size > 0 ? nb + 1 : 1;
+    int sot_index = -1;
+    for (int i = 0; i < n_initial; ++i) if (initial_tokens[i] == c.spec.sot) sot_index = i;   // tokens.index(sot) (:617)
+    // ---- state ----
+    DecodeState h{};
+    h.L = n_initial; h.pos = n_initial - 1; h.sample_begin = n_initial; h.sample_len = sample_len;
+    h.beam_mode = beam_size > 0; h.without_timestamps = without_timestamps; h.max_initial_ts = max_initial_timestamp_index;
+    h.suppress_blank = 1; h.no_speech_prob = NAN;
+    B200_CHECK(cudaMemcpyAsync(c.st, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    int* d_init = c.fin_tokens;                                         // scratch before any sequence finishes
+    B200_CHECK(cudaMemcpyAsync(d_init, initial_tokens, (size_t)n_initial * sizeof(int), cudaMemcpyHostToDevice, st));
+    init_tokens_kernel<<<1, 256, 0, st>>>(c.tokens, d_init, n_initial, nb, c.spec.eot, s.table);
+    B200_LAUNCH_CHECK();
+    {   // ---- prefill once: all beams hold the same initial tokens (decoding.py:761) ----
+        StageTimer t(ST_DECODER256);
+        prefill_inputs_kernel<<<PREFILL_CTX, 256, 0, st>>>(s.tok_emb, s.pos_emb, d_init, n_initial, d, s.px, s.pmask);
+        B200_LAUNCH_CHECK();
+        run_prefill(0, false);
+        init_tokens_kernel<<<1, 256, 0, st>>>(c.tokens, d_init, n_initial, nb, c.spec.eot, s.table);   // run_prefill marked slot 0 only
+        B200_LAUNCH_CHECK();
+        StepGemv g{};
+        g.nb = nb; g.w_frag = s.tok_emb_frag; g.N = s.V; g.K = d; g.x_f32 = s.pout + (size_t)(n_initial - 1) * d; g.ld_x = 0;
+        g.out_f32 = s.slogits; g.ld_out = s.V;
+        step_gemv(g, st);                                               // logits of the last prompt row, same for every beam
+        if (sot_index >= 0) {
+            g.nb = 1; g.x_f32 = s.pout + (size_t)sot_index * d; g.out_f32 = c.ns_logits;
+            step_gemv(g, st);
+            no_speech_prob(c.ns_logits, s.V, c.spec.no_speech, c.st, st);
+        }
+    }
+    {
+        StageTimer t(ST_SAMPLING);
+        launch_sampling(nb, k);
+    }
+    // ---- steps: i = 1 .. sample_len-1, polled every CHUNK steps for completion ----
+    const int CHUNK = 16;
+    int steps = 1;
+    bool done = false;
+    {
+        StageTimer t(ST_DECODER1);
+        while (!done && steps < sample_len) {
+            const int n = std::min(CHUNK, sample_len - steps);
+            for (int i = 0; i < n; ++i) {
+                step_embed(s.tok_emb, s.pos_emb, c.tokens, DEC_TOK_LD, 0, &c.st->pos, &c.st->done, nb, d, s.sx, st);
+                run_step(nb, 0, nullptr, true, &c.st->pos, &c.st->done);
+                launch_sampling(nb, k);
+            }
+            steps += n;
+            B200_CHECK(cudaMemcpyAsync(c.pin_done, &c.st->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+            B200_CHECK(cudaStreamSynchronize(st));
+            done = *c.pin_done != 0;
+        }
+    }
+    // ---- finalize (decoding.py:411-431 / :320-325) ----
+    std::vector<int> tok((size_t)DEC_MAX_BEAMS * DEC_TOK_LD), fin((size_t)DEC_MAX_BEAMS * DEC_TOK_LD);
+    B200_CHECK(cudaMemcpyAsync(&h, c.st, sizeof(h), cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaMemcpyAsync(tok.data(), c.tokens, tok.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaMemcpyAsync(fin.data(), c.fin_tokens, fin.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaStreamSynchronize(st));
+    const int eot = c.spec.eot;
+    int n_cand = 0;
+    auto emit = [&](const int* seq, int len, float score) {
+        int* dst = out_tokens + (size_t)n_cand * DEC_TOK_LD;
+        for (int i = 0; i < DEC_TOK_LD; ++i) dst[i] = i < len ? seq[i] : eot;
+        int l = 0;
+        while (n_initial + l < len && seq[n_initial + l] != eot) ++l;  // tokens before the first EOT after sample_begin (:776-779)
+        out_lengths[n_cand] = l; out_sum_logprobs[n_cand] = score; ++n_cand;
+    };
+    if (!h.beam_mode) {
+        emit(tok.data(), h.L, h.sum_lp[0]);
+    } else {
+        for (int f = 0; f < h.n_finished; ++f) emit(fin.data() + (size_t)f * DEC_TOK_LD, h.fin_len[f], h.fin_score[f]);
+        if (n_cand < nb) {                                              // not enough finished: add live beams, best first (:418-424)
+            std::vector<int> order(nb);
+            for (int i = 0; i < nb; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h.sum_lp[a] > h.sum_lp[b]; });
+            for (int i = 0; i < nb && n_cand < nb; ++i) emit(tok.data() + (size_t)order[i] * DEC_TOK_LD, h.L, h.sum_lp[order[i]]);
+        }
+    }
+    for (int i = n_cand; i < nb; ++i) { out_lengths[i] = -1; out_sum_logprobs[i] = -INFINITY; }
+    if (out_no_speech) *out_no_speech = h.no_speech_prob;
+    return h.step;
+}
+
+void decoder1StepFused(const int* tokens_hist, int n_hist, int sample_begin, int text_offset, int without_timestamps,
+                       int max_initial_timestamp_index, float* out_logprob, int* out_token) {
+    State& s = S();
+    DecodeCtx& c = g_dc;
+    if (!s.dec1_loaded || !s.dec256_loaded || !s.ckv_loaded) { record_error("decoder1StepFused: decoders not loaded"); return; }
+    if (n_hist < 1 || n_hist > N_TEXT_CTX || text_offset != n_hist - 1) { record_error("decoder1StepFused: n_hist %d / text_offset %d", n_hist, text_offset); return; }
+    use_device();
+    if (!ensure_decode_ctx()) return;
+    cudaStream_t st = s.stream;
+    const int nb = s.bs, k = nb + 1;
+    std::vector<int> rows((size_t)DEC_MAX_BEAMS * DEC_TOK_LD, c.spec.eot);
+    for (int b = 0; b < nb; ++b) memcpy(&rows[(size_t)b * DEC_TOK_LD], tokens_hist + (size_t)b * n_hist, (size_t)n_hist * sizeof(int));
+    B200_CHECK(cudaMemcpyAsync(c.tokens, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    DecodeState h{};
+    h.L = n_hist; h.pos = text_offset; h.sample_begin = sample_begin; h.sample_len = 1 << 30; h.beam_mode = 1;
+    h.without_timestamps = without_timestamps; h.max_initial_ts = max_initial_timestamp_index; h.suppress_blank = 1;
+    B200_CHECK(cudaMemcpyAsync(c.st, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    step_embed(s.tok_emb, s.pos_emb, c.tokens, DEC_TOK_LD, text_offset, nullptr, nullptr, nb, s.d, s.sx, st);
+    run_step(nb, text_offset, nullptr, true, nullptr, nullptr);
+    SampleArgs sa{};
+    sa.logits = s.slogits; sa.ld_logits = s.V; sa.tokens = c.tokens; sa.st = c.st; sa.spec = c.spec; sa.nb = nb; sa.k = k;
+    sa.cand_lp = c.cand_lp; sa.cand_tok = c.cand_tok;
+    sample_topk(sa, st);
+    B200_CHECK(cudaMemcpyAsync(out_logprob, c.cand_lp, (size_t)nb * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaMemcpyAsync(out_token, c.cand_tok, (size_t)nb * k * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaStreamSynchronize(st));
+}
+
+int b200AlignTokens(const int* tokens, int n_tokens, int n_skip, int num_frames, int medfilt_width, int* out_i, int* out_j,
+                    float* out_matrix, float* out_text_token_probs) {
+    State& s = S();
+    AlignCtx& a = g_al;
+    if (!s.dec256_loaded || !s.ckv_loaded) { record_error("b200AlignTokens: decoder256 / crossKV not loaded"); return 0; }
+    if (s.n_align < 1) { record_error("b200AlignTokens: loadDecoder256 was called with n_alignment_head = 0"); return 0; }
+    const int F = num_frames / 2, n_rows = n_tokens - 1 - n_skip, n_text = n_tokens - n_skip - 2;
+    if (n_tokens > PREFILL_CTX || n_rows < 1 || F < 1 || F > N_AUDIO_CTX) { record_error("b200AlignTokens: n_tokens %d n_skip %d num_frames %d", n_tokens, n_skip, num_frames); return 0; }
+    use_device();
+    cudaStream_t st = s.stream;
+    const size_t need = (size_t)2 * s.n_align * PREFILL_CTX * N_AUDIO_CTX;
+    if (!a.ready || a.tmp_cap < need) {
+        bool ok = true;
+        ok &= dev_alloc(&a.tmp, need); a.tmp_cap = need;
+        ok &= dev_alloc(&a.mat, (size_t)PREFILL_CTX * N_AUDIO_CTX); ok &= dev_alloc(&a.neg, (size_t)PREFILL_CTX * N_AUDIO_CTX);
+        ok &= dev_alloc(&a.logits, (size_t)PREFILL_CTX * ((s.V + 7) / 8 * 8)); ok &= dev_alloc(&a.probs, (size_t)PREFILL_CTX);
+        ok &= dev_alloc(&a.rows, (size_t)PREFILL_CTX * s.d); ok &= dev_alloc(&a.path, (size_t)2 * (PREFILL_CTX + N_AUDIO_CTX) + 1);
+        ok &= dev_alloc(&a.targets, (size_t)PREFILL_CTX); ok &= dev_alloc(&a.d_tok, (size_t)PREFILL_CTX);
+        ok &= dev_alloc(&a.scratch, dtw_scratch_bytes(PREFILL_CTX, N_AUDIO_CTX));
+        a.ready = ok;
+        if (!ok) return 0;
+    }
+    StageTimer timer(ST_ALIGN);
+    B200_CHECK(cudaMemcpyAsync(a.d_tok, tokens, (size_t)n_tokens * sizeof(int), cudaMemcpyHostToDevice, st));
+    prefill_inputs_kernel<<<PREFILL_CTX, 256, 0, st>>>(s.tok_emb, s.pos_emb, a.d_tok, n_tokens, s.d, s.px, s.pmask);
+    B200_LAUNCH_CHECK();
+    run_prefill(0, true);                                               // model(tokens[None]) (timing.py:185, model.py:110-119)
+    alignment_matrix_dev(s.pchw, s.n_align, PREFILL_CTX, n_tokens, F, n_skip, medfilt_width, a.tmp, a.mat, false, st);
+    negate_kernel<<<cdiv(n_rows * F, 256), 256, 0, st>>>(a.mat, a.neg, (long)n_rows * F);   // dtw(-matrix) (timing.py:205)
+    B200_LAUNCH_CHECK();
+    const int cap = n_rows + F;
+    B200_CHECK(cudaMemsetAsync(a.path + 2 * cap, 0, sizeof(int), st));
+    dtw_dev(a.neg, n_rows, F, a.path, a.path + cap, a.path + 2 * cap, a.scratch, st);
+    if (out_text_token_probs && n_text > 0) {                           // token_probs over [:eot] (timing.py:187-190)
+        f32_to_bf16(s.pout + (size_t)n_skip * s.d, a.rows, (long)n_text * s.d, st);
+        GemmParams g = gemm_plain(a.rows, s.tok_emb, a.logits, n_text, s.V, s.d);
+        g.c_fp32 = 1; g.ldc = (s.V + 7) / 8 * 8;                        // padded rows keep the epilogue stores vectorised
+        gemm_tcgen05(g, st);
+        B200_CHECK(cudaMemcpyAsync(a.targets, tokens + n_skip + 1, (size_t)n_text * sizeof(int), cudaMemcpyHostToDevice, st));
+        token_prob_kernel<<<n_text, 1024, 0, st>>>(a.logits, (s.V + 7) / 8 * 8, g_dc.spec.eot >= 0 ? g_dc.spec.eot : s.V, a.targets, a.probs);
+        B200_LAUNCH_CHECK();
+        B200_CHECK(cudaMemcpyAsync(out_text_token_probs, a.probs, (size_t)n_text * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    int len = 0;
+    B200_CHECK(cudaMemcpyAsync(&len, a.path + 2 * cap, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (out_matrix) B200_CHECK(cudaMemcpyAsync(out_matrix, a.mat, (size_t)n_rows * F * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaStreamSynchronize(st));
+    if (len > 0 && len <= cap) {
+        B200_CHECK(cudaMemcpy(out_i, a.path, (size_t)len * sizeof(int), cudaMemcpyDeviceToHost));
+        B200_CHECK(cudaMemcpy(out_j, a.path + cap, (size_t)len * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    return len;
+}
+
+void b200GetStageTimes(float* out_ms7, int reset) { stage_times(out_ms7, reset != 0); }
+
+}  // extern "C"

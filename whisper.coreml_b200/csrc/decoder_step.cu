@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(GV_THREADS, 3) step_gemv_kernel(const StepGemv
     const int ldx = g.K + GV_XPAD;
     float* red = reinterpret_cast<float*>(gv_smem + (size_t)8 * ldx * 2);   // [8 warps][128]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (g.d_skip && *g.d_skip) return;
 
     // ---- prologue: beam `warp` -> bf16 row in smem (rows >= nb are zero) ----
     {
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(128) step_self_attn_kernel(const StepSelfAttn 
     __shared__ float sred[4][64];
     __shared__ float sstat[8];
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t = a.text_offset, d = a.d;
+    if (a.d_skip && *a.d_skip) return;
+    const int t = a.d_text_offset ? *a.d_text_offset : a.text_offset, d = a.d;
     const float* row = a.qkv + (long)b * 3 * d + h * 64;
     if (tid < 64) {
         sq[tid] = row[tid];
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(CA_THREADS) step_cross_attn_kernel(const StepC
     __shared__ float sm[8], sl[8];
     __shared__ int s_last;
     const int h = blockIdx.x, sp_idx = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (a.d_skip && *a.d_skip) return;
     const int j0 = sp_idx * CA_KEYS, nk = min(CA_KEYS, a.n_keys - j0);
     for (int e = tid; e < 8 * 64; e += CA_THREADS) {
         const int b = e >> 6, c = e & 63;
@@ -309,15 +312,18 @@ void step_cross_attn(const StepCrossAttn& a, cudaStream_t s) {
 }
 
 __global__ void step_embed_kernel(const bf16* __restrict__ tok_emb, const float* __restrict__ pos_emb,
-                                  const int* __restrict__ tokens, long token_stride, int pos, int d, float* __restrict__ x) {
+                                  const int* __restrict__ tokens, long token_stride, int pos, const int* __restrict__ d_pos,
+                                  const int* __restrict__ d_skip, int d, float* __restrict__ x) {
+    if (d_skip && *d_skip) return;
+    if (d_pos) pos = *d_pos;
     const int b = blockIdx.x;
-    const int tok = tokens[b * token_stride];
+    const int tok = tokens[b * token_stride + pos];
     for (int c = threadIdx.x; c < d; c += blockDim.x)
         x[(long)b * d + c] = __bfloat162float(tok_emb[(long)tok * d + c]) + pos_emb[(long)pos * d + c];
 }
-void step_embed(const bf16* tok_emb, const float* pos_emb, const int* tokens, long token_stride, int pos, int nb, int d,
-                float* x, cudaStream_t s) {
-    step_embed_kernel<<<nb, 256, 0, s>>>(tok_emb, pos_emb, tokens, token_stride, pos, d, x);
+void step_embed(const bf16* tok_emb, const float* pos_emb, const int* tokens, long token_stride, int pos, const int* d_pos,
+                const int* d_skip, int nb, int d, float* x, cudaStream_t s) {
+    step_embed_kernel<<<nb, 256, 0, s>>>(tok_emb, pos_emb, tokens, token_stride, pos, d_pos, d_skip, d, x);
     B200_LAUNCH_CHECK();
 }
 

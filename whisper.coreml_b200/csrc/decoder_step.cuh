@@ -19,6 +19,7 @@ struct StepGemv {
     int gelu;
     const float* residual; long ld_res;    // fp32 [nb][ld_res] added to the output (may alias out_f32)
     float* out_f32; bf16* out_bf16; long ld_out;
+    const int* d_skip;         // device flag: non-zero -> the launch is a no-op (decode already complete)
 };
 void step_gemv(const StepGemv& g, cudaStream_t s);
 
@@ -28,6 +29,8 @@ struct StepSelfAttn {
     int* table;                // [slots][448] physical slot of logical (beam, position) (see api.cu: rearrange_mkv)
     const float* mask;         // (449) additive fp32 on the device or nullptr (all visible)
     int text_offset;           // number of cached positions; the new row is written at this index
+    const int* d_text_offset;  // if set, read the offset from device memory instead (graph replay)
+    const int* d_skip;
     int nb, n_head, d;
     bf16* out;                 // [nb][d]
 };
@@ -40,11 +43,13 @@ struct StepCrossAttn {
     float* part;               // scratch: [H][splits][8][66] (m, l, o[64])
     int* counters;             // [H], zero between launches
     bf16* out;                 // [nb][d]
+    const int* d_skip;
 };
 void step_cross_attn(const StepCrossAttn& a, cudaStream_t s);
 
 // x[b, :] = tok_emb[token[b], :] + pos_emb[pos, :]   (whisper/decoder.py:202), bf16 table, fp32 out
-void step_embed(const bf16* tok_emb, const float* pos_emb, const int* tokens, long token_stride, int pos, int nb, int d,
-                float* x, cudaStream_t s);
+// tokens: [nb][token_stride]; the token at column `pos` (or *d_pos) of each row is embedded at position `pos`.
+void step_embed(const bf16* tok_emb, const float* pos_emb, const int* tokens, long token_stride, int pos, const int* d_pos,
+                const int* d_skip, int nb, int d, float* x, cudaStream_t s);
 
 }  // namespace b200

@@ -35,6 +35,7 @@ struct GemmKernelArgs {
     int c_batch_rows, c_row0;
     int c_split;
     long c_split_stride;
+    int vec_ok;                 // output / residual rows are 16-byte aligned: 128-bit epilogue accesses allowed
 };
 
 template <int BLOCK_N, int STAGES>
@@ -133,11 +134,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 const int n0 = n_blk * BLOCK_N + c * 32;
                 if (!row_ok || n0 >= g.N) continue;
                 float v[32];
-                const bool full = n0 + 32 <= g.N;
+                const bool full = g.vec_ok && n0 + 32 <= g.N;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     float x = __uint_as_float(r[i]);
-                    if (g.bias && (full || n0 + i < g.N)) x += __ldg(g.bias + n0 + i);
+                    if (g.bias && n0 + i < g.N) x += __ldg(g.bias + n0 + i);
                     if (g.gelu) x = gelu_erf(x);
                     v[i] = x;
                 }
@@ -271,6 +272,9 @@ static void launch(const GemmParams& p, cudaStream_t stream) {
     g.N = p.N; g.bias = p.bias; g.gelu = p.gelu; g.add = p.add; g.add_rows = p.add_rows > 0 ? p.add_rows : 1;
     g.ld_add = p.ld_add; g.C = p.C; g.c_fp32 = p.c_fp32; g.ldc = p.ldc; g.c_batch_rows = p.c_batch_rows; g.c_row0 = p.c_row0;
     g.c_split = p.c_split; g.c_split_stride = p.c_split_stride;
+    const long c_elem = p.c_fp32 ? 4 : 2;
+    g.vec_ok = ((p.ldc * c_elem) % 16 == 0) && (((uintptr_t)p.C) % 16 == 0) && ((p.c_split_stride * c_elem) % 16 == 0) &&
+               (!p.add || (((p.ld_add * 4) % 16 == 0) && (((uintptr_t)p.add) % 16 == 0)));
 
     constexpr size_t smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
     static bool attr_set = false;

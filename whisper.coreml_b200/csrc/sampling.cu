@@ -1,0 +1,252 @@
+#include "sampling.cuh"
+
+namespace b200 {
+
+constexpr int SM_THREADS = 1024;
+
+struct Rules {
+    int at_begin, last_ts, penult_ts, last_stamp, lim;
+};
+
+__device__ __forceinline__ bool is_masked(int v, const DecodeSpec& sp, const DecodeState& st, const Rules& r) {
+    if (sp.d_suppress[v]) return true;                                              // SuppressTokens (:460-465)
+    if (r.at_begin && st.suppress_blank &&
+        (v == sp.eot || v == sp.blank[0] || v == sp.blank[1] || v == sp.blank[2] || v == sp.blank[3]))
+        return true;                                                                // SuppressBlank (:450-457)
+    if (st.without_timestamps) return false;
+    const int tb = sp.timestamp_begin;                                              // ApplyTimestampRules (:468-523)
+    if (v == sp.no_timestamps) return true;
+    if (r.last_ts) {
+        if (r.penult_ts) { if (v >= tb) return true; }
+        else if (v < sp.eot) return true;
+    }
+    if (r.last_stamp >= 0 && v >= tb && v < r.lim) return true;
+    if (r.at_begin) {
+        if (v < tb) return true;
+        if (st.max_initial_ts >= 0 && v > tb + st.max_initial_ts) return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ void online_add(float& m, float& s, float x) {
+    if (x == -INFINITY) return;
+    if (x > m) { s = s * __expf(m - x) + 1.f; m = x; }
+    else s += __expf(x - m);
+}
+__device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
+    if (m2 == -INFINITY) return;
+    if (m == -INFINITY) { m = m2; s = s2; return; }
+    const float M = fmaxf(m, m2);
+    s = s * __expf(m - M) + s2 * __expf(m2 - M);
+    m = M;
+}
+
+__global__ void __launch_bounds__(SM_THREADS) sample_topk_kernel(const SampleArgs a) {
+    __shared__ Rules rules;
+    __shared__ float red_m[2][32], red_s[2][32];
+    __shared__ float arg_v[32]; __shared__ int arg_i[32];
+    __shared__ int chosen[DEC_MAX_BEAMS + 1];
+    __shared__ float s_lse; __shared__ int s_mask_text;
+    const DecodeState& st = *a.st;
+    if (st.done) return;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DecodeSpec& sp = a.spec;
+    const int V = sp.n_vocab, tb = sp.timestamp_begin;
+    float* x = a.logits + (long)b * a.ld_logits;
+    if (tid == 0) {
+        Rules r;
+        const int* seq = a.tokens + b * DEC_TOK_LD + st.sample_begin;
+        const int n = st.L - st.sample_begin;
+        r.at_begin = n == 0;
+        r.last_ts = n >= 1 && seq[n - 1] >= tb;
+        r.penult_ts = n < 2 || seq[n - 2] >= tb;
+        r.last_stamp = -1;
+        for (int j = 0; j < n; ++j) if (seq[j] >= tb) r.last_stamp = seq[j];
+        r.lim = (r.last_ts && !r.penult_ts) ? r.last_stamp : r.last_stamp + 1;
+        rules = r;
+    }
+    __syncthreads();
+    const Rules r = rules;
+    // ---- pass 1: filters + online (max, sum exp) for the text and the timestamp groups --------------
+    float mt = -INFINITY, stx = 0.f, mq = -INFINITY, sq = 0.f;
+    for (int v = tid; v < V; v += SM_THREADS) {
+        float val = x[v];
+        if (is_masked(v, sp, st, r)) { val = -INFINITY; x[v] = val; }
+        if (v < tb) online_add(mt, stx, val); else online_add(mq, sq, val);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        online_merge(mt, stx, __shfl_xor_sync(0xffffffffu, mt, o), __shfl_xor_sync(0xffffffffu, stx, o));
+        online_merge(mq, sq, __shfl_xor_sync(0xffffffffu, mq, o), __shfl_xor_sync(0xffffffffu, sq, o));
+    }
+    if (lane == 0) { red_m[0][warp] = mt; red_s[0][warp] = stx; red_m[1][warp] = mq; red_s[1][warp] = sq; }
+    __syncthreads();
+    if (warp == 0) {
+        mt = red_m[0][lane]; stx = red_s[0][lane]; mq = red_m[1][lane]; sq = red_s[1][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            online_merge(mt, stx, __shfl_xor_sync(0xffffffffu, mt, o), __shfl_xor_sync(0xffffffffu, stx, o));
+            online_merge(mq, sq, __shfl_xor_sync(0xffffffffu, mq, o), __shfl_xor_sync(0xffffffffu, sq, o));
+        }
+        if (lane == 0) {
+            const float lse_t = mt == -INFINITY ? -INFINITY : mt + logf(stx);
+            const float lse_q = mq == -INFINITY ? -INFINITY : mq + logf(sq);
+            float ma = mt, sa = stx;
+            online_merge(ma, sa, mq, sq);
+            const float lse_all = ma == -INFINITY ? -INFINITY : ma + logf(sa);
+            // "if sum of probability over timestamps is above any other token, sample timestamp" (:525-532)
+            int mask_text = 0;
+            if (!st.without_timestamps) mask_text = (lse_q - lse_all) > (mt - lse_all);
+            s_mask_text = mask_text;
+            s_lse = mask_text ? lse_q : lse_all;
+        }
+    }
+    __syncthreads();
+    const int v0 = s_mask_text ? tb : 0;
+    if (s_mask_text)
+        for (int v = tid; v < tb; v += SM_THREADS) x[v] = -INFINITY;
+    // ---- pass 2: top-k by repeated block arg-max (ties -> lowest index) ----------------------------------
+    for (int c = 0; c < a.k; ++c) {
+        float bv = -INFINITY; int bi = 0x7fffffff;
+        for (int v = v0 + tid; v < V; v += SM_THREADS) {
+            bool taken = false;
+            for (int q = 0; q < c; ++q) taken |= (chosen[q] == v);
+            if (taken) continue;
+            const float val = x[v];
+            if (val > bv || (val == bv && v < bi)) { bv = val; bi = v; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { arg_v[warp] = bv; arg_i[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            bv = arg_v[lane]; bi = arg_i[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) {
+                chosen[c] = bi;
+                a.cand_tok[b * a.k + c] = bi;
+                a.cand_lp[b * a.k + c] = bv - s_lse;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+void sample_topk(const SampleArgs& a, cudaStream_t s) {
+    sample_topk_kernel<<<a.nb, SM_THREADS, 0, s>>>(a);
+    B200_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GreedyDecoder.update (:303-318) / BeamSearchDecoder.update (:350-409), one CTA.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) beam_update_kernel(const BeamUpdateArgs a) {
+    __shared__ int stage[DEC_MAX_BEAMS * DEC_TOK_LD];
+    __shared__ int nsrc[DEC_MAX_BEAMS], ntok[DEC_MAX_BEAMS];
+    __shared__ float nsum[DEC_MAX_BEAMS];
+    __shared__ int fin_src[DEC_MAX_BEAMS]; __shared__ float fin_sc[DEC_MAX_BEAMS];
+    __shared__ int s_nfin_new, s_done;
+    DecodeState& st = *a.st;
+    if (st.done) return;
+    const int tid = threadIdx.x, nb = a.nb, L = st.L;
+    if (tid == 0) {
+        int nfin_new = 0, done = 0;
+        if (!st.beam_mode) {
+            const int tok = a.cand_tok[0], last = a.tokens[L - 1];
+            nsrc[0] = 0;
+            ntok[0] = last == a.eot ? a.eot : tok;
+            nsum[0] = st.sum_lp[0] + (last == a.eot ? 0.f : a.cand_lp[0]);
+            done = ntok[0] == a.eot;
+        } else {
+            const int nsb = st.step == 0 ? 1 : nb;      // identical prefixes at step 0 collapse to one key set (:366-373)
+            const int n = nsb * a.k;
+            float sc[DEC_MAX_BEAMS * (DEC_MAX_BEAMS + 1)]; int id[DEC_MAX_BEAMS * (DEC_MAX_BEAMS + 1)];
+            for (int j = 0; j < nsb; ++j)
+                for (int c = 0; c < a.k; ++c) { sc[j * a.k + c] = st.sum_lp[j] + a.cand_lp[j * a.k + c]; id[j * a.k + c] = j * a.k + c; }
+            for (int i = 1; i < n; ++i) {                // stable insertion sort, descending (:377)
+                const float s = sc[i]; const int d = id[i];
+                int p = i - 1;
+                while (p >= 0 && sc[p] < s) { sc[p + 1] = sc[p]; id[p + 1] = id[p]; --p; }
+                sc[p + 1] = s; id[p + 1] = d;
+            }
+            int cnt = 0;
+            for (int i = 0; i < n && cnt < nb; ++i) {
+                const int j = id[i] / a.k, tok = a.cand_tok[id[i]];
+                if (tok == a.eot) { if (nfin_new < DEC_MAX_BEAMS) { fin_src[nfin_new] = j; fin_sc[nfin_new] = sc[i]; ++nfin_new; } }
+                else { nsrc[cnt] = j; ntok[cnt] = tok; nsum[cnt] = sc[i]; ++cnt; }
+            }
+            for (; cnt < nb; ++cnt) { nsrc[cnt] = nsrc[cnt > 0 ? cnt - 1 : 0]; ntok[cnt] = ntok[cnt > 0 ? cnt - 1 : 0]; nsum[cnt] = -INFINITY; }
+        }
+        s_nfin_new = nfin_new; s_done = done;
+    }
+    __syncthreads();
+    // finished pool: at most max_candidates (= nb, patience 1) sequences, best first (:396-402)
+    const int max_cand = nb;
+    int nfin = st.n_finished;
+    for (int f = 0; f < s_nfin_new && nfin < max_cand; ++f, ++nfin) {
+        const int* src = a.tokens + fin_src[f] * DEC_TOK_LD;
+        int* dst = a.fin_tokens + nfin * DEC_TOK_LD;
+        for (int i = tid; i < L; i += blockDim.x) dst[i] = src[i];
+        if (tid == 0) { dst[L] = a.eot; st.fin_len[nfin] = L + 1; st.fin_score[nfin] = fin_sc[f]; }
+    }
+    __syncthreads();
+    // permute token histories and KV slot tables by source beam, append the new tokens
+    for (int i = tid; i < nb * DEC_TOK_LD; i += blockDim.x) stage[i] = a.tokens[i];
+    __syncthreads();
+    for (int i = tid; i < nb * L; i += blockDim.x) {
+        const int bb = i / L, p = i % L;
+        a.tokens[bb * DEC_TOK_LD + p] = stage[nsrc[bb] * DEC_TOK_LD + p];
+    }
+    __syncthreads();
+    for (int i = tid; i < nb * 448; i += blockDim.x) stage[i] = a.table[i];
+    __syncthreads();
+    for (int i = tid; i < nb * L; i += blockDim.x) {
+        const int bb = i / L, p = i % L;
+        if (p < 448) a.table[bb * 448 + p] = stage[nsrc[bb] * 448 + p];
+    }
+    if (tid < nb) { a.tokens[tid * DEC_TOK_LD + L] = ntok[tid]; st.sum_lp[tid] = nsum[tid]; }
+    __syncthreads();
+    if (tid == 0) {
+        st.n_finished = nfin;
+        st.L = L + 1; st.pos = L; st.step += 1;
+        int done = s_done;
+        if (st.beam_mode && nfin >= max_cand) done = 1;
+        if (L + 1 > a.n_text_ctx) done = 1;                              // :732
+        if (st.step >= st.sample_len) done = 1;
+        st.done = done;
+    }
+}
+
+void beam_update(const BeamUpdateArgs& a, cudaStream_t s) {
+    beam_update_kernel<<<1, 256, 0, s>>>(a);
+    B200_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(1024) no_speech_kernel(const float* __restrict__ x, int V, int tok, DecodeState* st) {
+    __shared__ float rm[32], rs[32];
+    float m = -INFINITY, s = 0.f;
+    for (int v = threadIdx.x; v < V; v += 1024) online_add(m, s, x[v]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) online_merge(m, s, __shfl_xor_sync(0xffffffffu, m, o), __shfl_xor_sync(0xffffffffu, s, o));
+    if ((threadIdx.x & 31) == 0) { rm[threadIdx.x >> 5] = m; rs[threadIdx.x >> 5] = s; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = rm[threadIdx.x]; s = rs[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) online_merge(m, s, __shfl_xor_sync(0xffffffffu, m, o), __shfl_xor_sync(0xffffffffu, s, o));
+        if (threadIdx.x == 0) st->no_speech_prob = expf(x[tok] - m) / s;
+    }
+}
+void no_speech_prob(const float* logits, int n_vocab, int no_speech, DecodeState* st, cudaStream_t s) {
+    no_speech_kernel<<<1, 1024, 0, s>>>(logits, n_vocab, no_speech, st);
+    B200_LAUNCH_CHECK();
+}
+
+}  // namespace b200

@@ -1,0 +1,54 @@
+// Device-side logit filters, log-softmax, top-k and greedy / beam-search bookkeeping
+// (whisper/decoding.py:299-431, 450-532), so that a whole DecodingTask._main_loop (:707-737) runs
+// without a host round trip per token.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int DEC_MAX_BEAMS = 8;
+constexpr int DEC_TOK_LD = 449;        // n_text_ctx + 1
+
+struct DecodeSpec {                    // token ids (whisper/tokenizer.py), set by b200SetDecodeSpec
+    int sot = -1, eot = -1, no_timestamps = -1, timestamp_begin = -1, no_speech = -1, n_vocab = 0;
+    int blank[4] = {-1, -1, -1, -1};
+    const uint8_t* d_suppress = nullptr;   // [n_vocab] 1 = SuppressTokens member
+};
+
+struct DecodeState {                   // one per decode, in device memory
+    int L;                             // tokens per beam so far
+    int pos;                           // text_offset of the next decoder1 step (= L - 1)
+    int step;                          // loop index i of _main_loop
+    int done;
+    int n_finished;
+    int sample_begin, sample_len, beam_mode, without_timestamps, max_initial_ts, suppress_blank;
+    float no_speech_prob;
+    float sum_lp[DEC_MAX_BEAMS];
+    float fin_score[DEC_MAX_BEAMS];
+    int fin_len[DEC_MAX_BEAMS];
+};
+
+struct SampleArgs {
+    float* logits; long ld_logits;     // [nb][V]; overwritten with the filtered logits
+    const int* tokens;                 // [nb][DEC_TOK_LD]
+    DecodeState* st;
+    DecodeSpec spec;
+    int nb, k;                         // k = nb + 1 candidates per beam (1 for greedy)
+    float* cand_lp; int* cand_tok;     // [nb][k]
+};
+void sample_topk(const SampleArgs& a, cudaStream_t s);
+
+struct BeamUpdateArgs {
+    const float* cand_lp; const int* cand_tok; int nb, k;
+    int* tokens;                       // [nb][DEC_TOK_LD], permuted + extended in place
+    int* table;                        // [nb][448] KV slot table, permuted in place
+    int* fin_tokens;                   // [DEC_MAX_BEAMS][DEC_TOK_LD]
+    DecodeState* st;
+    int eot, n_text_ctx;
+};
+void beam_update(const BeamUpdateArgs& a, cudaStream_t s);
+
+// st->no_speech_prob = softmax(logits)[no_speech]   (whisper/decoding.py:716-720)
+void no_speech_prob(const float* logits, int n_vocab, int no_speech, DecodeState* st, cudaStream_t s);
+
+}  // namespace b200

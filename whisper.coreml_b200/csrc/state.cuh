@@ -23,7 +23,7 @@ struct DecLayer {
 
 struct State {
     int device = 0;
-    cudaStream_t stream = 0;          // legacy default stream: ordered with the caller's torch work
+    cudaStream_t stream = nullptr;    // library stream (non-blocking, capturable); created by use_device()
 
     // ---- encoder -------------------------------------------------------------------------------
     bool enc_loaded = false;
@@ -57,7 +57,6 @@ struct State {
     std::vector<DecLayer> dec_layers;
     bf16* mkv = nullptr;              // [2Ld][bs][448][d]
     int* table = nullptr;             // [bs][448] logical (beam, pos) -> physical slot
-    std::vector<int> h_table;
     std::vector<int> align_heads;     // (layer, head) pairs in CHW row order; empty = default
     int* d_dump_slot = nullptr;       // [Ld][H] CHW row of each head or -1
     // prefill workspace (256 rows)
@@ -90,11 +89,23 @@ bool dev_alloc(T** p, size_t n, bool zero = false) {
 template <typename T>
 void dev_free(T** p) { if (*p) { B200_CHECK(cudaFree(*p)); *p = nullptr; } }
 
-// sub-model bodies (api_models.cu)
+void use_device();
+
+// per-stage device time (CUDA events), the analogue of whisper/coreml.py:9-13
+enum Stage { ST_MEL = 0, ST_ENCODER, ST_CROSSKV, ST_DECODER256, ST_DECODER1, ST_SAMPLING, ST_ALIGN, ST_COUNT };
+struct StageTimer {
+    StageTimer(int stage);
+    ~StageTimer();
+    int stage; cudaEvent_t e0, e1;
+};
+void stage_times(float* out_ms, bool reset);
+
+// sub-model bodies (api.cu)
 bool ensure_encoder_capacity(int n_windows);
 void run_encoder(const float* d_mel, long total_frames, int n_windows);   // seeks already in S().d_seeks
 void run_cross_kv(int n_windows);
 void run_prefill(int beam_idx, bool want_chw);                            // px/pmask -> pout (+ pchw), KV rows -> slot
-void run_step(int nb, int text_offset, const float* d_mask, bool want_logits);   // sx -> slogits
+// sx -> slogits; d_t / d_skip: optional device-side text_offset and no-op flag (device-driven decode loop)
+void run_step(int nb, int text_offset, const float* d_mask, bool want_logits, const int* d_t, const int* d_skip);
 
 }  // namespace b200
