@@ -172,10 +172,12 @@ class Result:
     trace: List[List[int]]        # per-step beam token matrix (last column), for parity debugging
 
 
-def decode_window(model: OracleModel, mel: torch.Tensor, sp: Specials, opt: Options) -> Result:
-    """DecodingTask.run + _main_loop (decoding.py:707-816) for one 30-s window, temperature 0."""
+def decode_window(model: OracleModel, mel: Optional[torch.Tensor], sp: Specials, opt: Options) -> Result:
+    """DecodingTask.run + _main_loop (decoding.py:707-816) for one 30-s window, temperature 0.
+    mel=None reuses the encoder output already held by `model` (lets bench.py time the stages apart)."""
     model.reset()
-    model.encode(mel)
+    if mel is not None:
+        model.encode(mel)
     sot_seq = list(sp.sot_sequence) + ([sp.no_timestamps] if opt.without_timestamps else [])
     initial = list(sot_seq)
     if opt.prompt:      # :628-638 - fixed-window sharding runs condition_on_previous_text=False

@@ -64,11 +64,13 @@ def transcribe(model, audio: torch.Tensor, *, beam_size: Optional[int] = 5, word
     opts = DecodingOptions(beam_size=beam_size, sample_len=sample_len, without_timestamps=without_timestamps,
                            length_penalty=length_penalty)
     segments: List[dict] = []
+    decode_steps: List[int] = []
     for b0 in range(0, len(mine), window_batch):
         batch = mine[b0:b0 + window_batch]
         model.encode_windows(mel, batch)
         for w, seek in enumerate(batch):
             result = decode(model, opts, window=w)
+            decode_steps.append(result.steps)
             segment_size = min(N_FRAMES, content_frames - seek)
             time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
             if not result.tokens:
@@ -100,7 +102,7 @@ def transcribe(model, audio: torch.Tensor, *, beam_size: Optional[int] = 5, word
     for i, s in enumerate(segments):
         s["id"] = i
     out = {"segments": segments, "windows": len(mine), "seeks": mine, "language": "en",
-           "audio_seconds": audio.numel() / SAMPLE_RATE}
+           "audio_seconds": audio.numel() / SAMPLE_RATE, "decode_steps": decode_steps}
     if tokenizer is not None:
         out["text"] = "".join(s.get("text", "") for s in segments)
     return out
