@@ -158,6 +158,9 @@ void b200TestGemm(const void* dA, const void* dB, const float* dBias, void* dC, 
 void b200TestGetXa(float* out, int w);
 void b200TestGetCrossKV(float* out_ck, float* out_cv, int w);
 void b200TestGetKV(float* out, int n_rows);
+/* softmax(Q K^T) V per head over a fused DEVICE [batch][n_tok][3*heads*64] bf16 QKV buffer ->
+ * [batch][n_tok][heads*64] bf16: the tcgen05 flash-attention kernel, or the SIMT checker. */
+void b200TestAttention(const void* dQKV, void* dO, int n_tok, int heads, int batch, int use_simt);
 
 #if __cplusplus
 }

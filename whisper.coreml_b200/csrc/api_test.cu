@@ -74,3 +74,19 @@ extern "C" void b200TestGetKV(float* out, int n_rows) {
                 for (int c = 0; c < s.d; ++c) dst[c] = __bfloat162float(src[c]);
             }
 }
+
+// softmax(Q K^T) V per head over a fused [batch][n_tok][3 * heads * 64] bf16 QKV buffer (device), output
+// [batch][n_tok][heads * 64] bf16; tcgen05 kernel or the SIMT checker.
+extern "C" void b200TestAttention(const void* dQKV, void* dO, int n_tok, int heads, int batch, int use_simt) {
+    use_device();
+    const long d = (long)heads * 64;
+    AttnParams a{};
+    a.Q = (const bf16*)dQKV; a.K = a.Q + d; a.V = a.Q + 2 * d;
+    a.ldq = a.ldk = a.ldv = 3 * d; a.q_head_stride = a.k_head_stride = a.v_head_stride = 64;
+    a.q_batch_stride = a.k_batch_stride = a.v_batch_stride = (long)n_tok * 3 * d;
+    a.O = (bf16*)dO; a.ldo = d; a.o_head_stride = 64; a.o_batch_stride = (long)n_tok * d;
+    a.n_q = a.n_k = n_tok; a.n_head = heads; a.batch = batch;
+    B200_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
+    if (use_simt) attention_simt(a, S().stream); else attention_tc(a, S().stream);
+    B200_CHECK(cudaStreamSynchronize(S().stream));
+}

@@ -221,7 +221,3 @@ void attention_simt(const AttnParams& p, cudaStream_t s) {
 
 }  // namespace b200
 
-namespace b200 {
-// Until the tcgen05 kernel lands in attention.cu this forwards to the SIMT kernel.
-__attribute__((weak)) void attention_tc(const AttnParams& p, cudaStream_t s) { attention_simt(p, s); }
-}  // namespace b200
