@@ -12,6 +12,8 @@ namespace b200 {
 
 int take_errors(char*, int);
 void gemm_clear_map_cache();
+void attention_clear_map_cache();
+void decode_clear_graphs();
 
 State& S() { static State s; return s; }
 
@@ -43,7 +45,7 @@ bool ensure_encoder_capacity(int W) {
     dev_free(&s.xa);
     s.xa = new_xa;
     ok &= dev_alloc(&s.d_seeks, (size_t)W);
-    gemm_clear_map_cache();
+    gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
     if (ok) s.w_cap = W;
     return ok;
 }
@@ -112,7 +114,7 @@ void run_cross_kv(int W) {
     if (W > s.ckv_cap) {
         if (!dev_alloc(&s.ckv, (size_t)W * s.ckv_window_elems())) return;
         s.ckv_cap = W;
-        gemm_clear_map_cache();
+        gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
     }
     const int d = s.d;
     GemmParams p{};
@@ -350,7 +352,7 @@ void closeEncoder() {
     dev_free(&s.melrows); dev_free(&s.h1); dev_free(&s.x); dev_free(&s.y); dev_free(&s.qkv); dev_free(&s.att);
     dev_free(&s.hid); dev_free(&s.xa); dev_free(&s.mel_stage); dev_free(&s.d_seeks);
     s.enc_w.unload(); s.enc_layers.clear(); s.w_cap = 0; s.n_windows = 0; s.enc_loaded = false;
-    gemm_clear_map_cache();
+    gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
 }
 
 void encoderPredict(float* melSegment) {
@@ -385,7 +387,7 @@ void closeCrossKV() {
     use_device();
     B200_CHECK(cudaDeviceSynchronize());
     dev_free(&s.ckv); s.ckv_cap = 0; s.ckv_w.unload(); s.ckv_loaded = false;
-    gemm_clear_map_cache();
+    gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
 }
 
 void crossKVPredict() {
@@ -427,7 +429,7 @@ void closeDecoder256() {
     dev_free(&s.py); dev_free(&s.pqkv); dev_free(&s.patt); dev_free(&s.phid); dev_free(&s.pq); dev_free(&s.d_dump_slot);
     release_decoder_weights();
     s.dec256_loaded = false;
-    gemm_clear_map_cache();
+    gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
 }
 
 void decoder256Predict(float* x, float* qk_mask, float* out_x, float* out_cross_head_weights, int beam_idx) {
@@ -471,6 +473,7 @@ void closeDecoder1() {
     B200_CHECK(cudaDeviceSynchronize());
     dev_free(&s.sx); dev_free(&s.sqkv); dev_free(&s.sq); dev_free(&s.slogits); dev_free(&s.smask); dev_free(&s.spart);
     dev_free(&s.scounters); dev_free(&s.satt); dev_free(&s.shid);
+    decode_clear_graphs();
     release_decoder_weights();
     s.dec1_loaded = false;
 }

@@ -2,6 +2,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <tuple>
 #include <vector>
 
 #include "decoder_step.cuh"
@@ -22,6 +24,7 @@ struct DecodeCtx {
     int* tokens = nullptr;              // [8][449]
     int* fin_tokens = nullptr;          // [8][449]
     float* cand_lp = nullptr; int* cand_tok = nullptr;   // [8][9]
+    SamplePartials* part = nullptr;
     float* ns_logits = nullptr;         // [V] logits at the sot position
     int* pin_done = nullptr;            // pinned host
     bool ready = false;
@@ -40,6 +43,7 @@ static bool ensure_decode_ctx() {
     ok &= dev_alloc(&c.cand_lp, (size_t)DEC_MAX_BEAMS * (DEC_MAX_BEAMS + 1));
     ok &= dev_alloc(&c.cand_tok, (size_t)DEC_MAX_BEAMS * (DEC_MAX_BEAMS + 1));
     ok &= dev_alloc(&c.ns_logits, (size_t)s.V);
+    ok &= dev_alloc(&c.part, 1, true);
     if (!c.pin_done) ok &= cudaMallocHost((void**)&c.pin_done, 64) == cudaSuccess;
     c.ready = ok;
     return ok;
@@ -81,14 +85,53 @@ __global__ void negate_kernel(const float* __restrict__ in, float* __restrict__ 
 __global__ void token_prob_kernel(const float* __restrict__ logits, long ld, int eot, const int* __restrict__ targets,
                                   float* __restrict__ out);
 
+// ---- CUDA graphs of GRAPH_STEPS decoder1 iterations (embed -> blocks -> vocab -> sampling -> beam update) --------
+// Every per-step quantity (text_offset, tokens, slot table, completion flag) lives in device memory, so one
+// instantiated graph serves every step of every window that uses the same buffers.
+constexpr int GRAPH_STEPS = 8;
+struct StepGraph { cudaGraphExec_t exec = nullptr; long launches = 0; };
+static std::map<std::tuple<int, int, const void*, const void*, const void*>, StepGraph> g_step_graphs;
+void decode_clear_graphs() {
+    for (auto& kv : g_step_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    g_step_graphs.clear();
+}
+
+static void launch_sampling(int nb, int k);
+static void one_step(int nb, int k) {
+    State& s = S();
+    DecodeCtx& c = g_dc;
+    step_embed(s.tok_emb, s.pos_emb, c.tokens, DEC_TOK_LD, 0, &c.st->pos, &c.st->done, nb, s.d, s.sx, s.stream);
+    run_step(nb, 0, nullptr, true, &c.st->pos, &c.st->done);
+    launch_sampling(nb, k);
+}
+
+static StepGraph* step_graph(int nb, int k) {
+    State& s = S();
+    auto key = std::make_tuple(nb, k, (const void*)s.ck_ptr(s.cur_window, 0), (const void*)s.mkv, (const void*)s.slogits);
+    auto it = g_step_graphs.find(key);
+    if (it != g_step_graphs.end()) return &it->second;
+    cudaGraph_t graph = nullptr;
+    const long l0 = g_launch_count;
+    if (cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    for (int i = 0; i < GRAPH_STEPS; ++i) one_step(nb, k);
+    StepGraph g;
+    g.launches = g_launch_count - l0;
+    g_launch_count = l0;                                               // capture issued nothing; replays are counted per launch
+    if (cudaStreamEndCapture(s.stream, &graph) != cudaSuccess || !graph) { cudaGetLastError(); return nullptr; }
+    if (cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(graph); return nullptr; }
+    cudaGraphDestroy(graph);
+    return &g_step_graphs.emplace(key, g).first->second;
+}
+
 static void launch_sampling(int nb, int k) {
     State& s = S();
     DecodeCtx& c = g_dc;
     SampleArgs sa{};
     sa.logits = s.slogits; sa.ld_logits = s.V; sa.tokens = c.tokens; sa.st = c.st; sa.spec = c.spec; sa.nb = nb; sa.k = k;
-    sa.cand_lp = c.cand_lp; sa.cand_tok = c.cand_tok;
-    sample_topk(sa, s.stream);
+    sa.cand_lp = c.cand_lp; sa.cand_tok = c.cand_tok; sa.part = c.part;
+    sample_partial(sa, s.stream);
     BeamUpdateArgs ba{};
+    ba.part = c.part; ba.timestamp_begin = c.spec.timestamp_begin; ba.update = 1;
     ba.cand_lp = c.cand_lp; ba.cand_tok = c.cand_tok; ba.nb = nb; ba.k = k; ba.tokens = c.tokens; ba.table = s.table;
     ba.fin_tokens = c.fin_tokens; ba.st = c.st; ba.eot = c.spec.eot; ba.n_text_ctx = N_TEXT_CTX;
     beam_update(ba, s.stream);
@@ -193,19 +236,17 @@ int b200DecodeWindow(const int* initial_tokens, int n_initial, int beam_size, in
         launch_sampling(nb, k);
     }
     // ---- steps: i = 1 .. sample_len-1, polled every CHUNK steps for completion ----
-    const int CHUNK = 16;
     int steps = 1;
     bool done = false;
     {
         StageTimer t(ST_DECODER1);
+        if (steps < sample_len) { one_step(nb, k); ++steps; }           // eager once: sets kernel attributes before any capture
+        StepGraph* g = steps < sample_len ? step_graph(nb, k) : nullptr;
         while (!done && steps < sample_len) {
-            const int n = std::min(CHUNK, sample_len - steps);
-            for (int i = 0; i < n; ++i) {
-                step_embed(s.tok_emb, s.pos_emb, c.tokens, DEC_TOK_LD, 0, &c.st->pos, &c.st->done, nb, d, s.sx, st);
-                run_step(nb, 0, nullptr, true, &c.st->pos, &c.st->done);
-                launch_sampling(nb, k);
-            }
-            steps += n;
+            // launches past sample_len / completion are no-ops: every kernel checks DecodeState::done first
+            if (g) { B200_CHECK(cudaGraphLaunch(g->exec, st)); g_launch_count += g->launches; }
+            else for (int i = 0; i < GRAPH_STEPS; ++i) one_step(nb, k);
+            steps += GRAPH_STEPS;
             B200_CHECK(cudaMemcpyAsync(c.pin_done, &c.st->done, sizeof(int), cudaMemcpyDeviceToHost, st));
             B200_CHECK(cudaStreamSynchronize(st));
             done = *c.pin_done != 0;
@@ -263,8 +304,13 @@ void decoder1StepFused(const int* tokens_hist, int n_hist, int sample_begin, int
     run_step(nb, text_offset, nullptr, true, nullptr, nullptr);
     SampleArgs sa{};
     sa.logits = s.slogits; sa.ld_logits = s.V; sa.tokens = c.tokens; sa.st = c.st; sa.spec = c.spec; sa.nb = nb; sa.k = k;
-    sa.cand_lp = c.cand_lp; sa.cand_tok = c.cand_tok;
-    sample_topk(sa, st);
+    sa.cand_lp = c.cand_lp; sa.cand_tok = c.cand_tok; sa.part = c.part;
+    sample_partial(sa, st);
+    BeamUpdateArgs ba{};
+    ba.part = c.part; ba.timestamp_begin = c.spec.timestamp_begin; ba.update = 0;
+    ba.cand_lp = c.cand_lp; ba.cand_tok = c.cand_tok; ba.nb = nb; ba.k = k; ba.tokens = c.tokens; ba.table = s.table;
+    ba.fin_tokens = c.fin_tokens; ba.st = c.st; ba.eot = c.spec.eot; ba.n_text_ctx = N_TEXT_CTX;
+    beam_update(ba, st);
     B200_CHECK(cudaMemcpyAsync(out_logprob, c.cand_lp, (size_t)nb * k * sizeof(float), cudaMemcpyDeviceToHost, st));
     B200_CHECK(cudaMemcpyAsync(out_token, c.cand_tok, (size_t)nb * k * sizeof(int), cudaMemcpyDeviceToHost, st));
     B200_CHECK(cudaStreamSynchronize(st));

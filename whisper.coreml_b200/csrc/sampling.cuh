@@ -28,18 +28,30 @@ struct DecodeState {                   // one per decode, in device memory
     int fin_len[DEC_MAX_BEAMS];
 };
 
+// Phase 1: the vocabulary is cut into SAMPLE_TEXT_CHUNKS text chunks + 1 timestamp chunk per beam (one CTA each, so
+// a 5-beam step fills the GPU); each CTA applies the logit filters and leaves (max, sum exp) and its top-k.
+constexpr int SAMPLE_TEXT_CHUNKS = 28, SAMPLE_CHUNKS = SAMPLE_TEXT_CHUNKS + 1, SAMPLE_MAX_K = DEC_MAX_BEAMS + 1;
+struct SamplePartials {                // device scratch
+    float m[DEC_MAX_BEAMS][SAMPLE_CHUNKS], s[DEC_MAX_BEAMS][SAMPLE_CHUNKS];
+    float topv[DEC_MAX_BEAMS][SAMPLE_CHUNKS][SAMPLE_MAX_K];
+    int topi[DEC_MAX_BEAMS][SAMPLE_CHUNKS][SAMPLE_MAX_K];
+};
 struct SampleArgs {
-    float* logits; long ld_logits;     // [nb][V]; overwritten with the filtered logits
+    const float* logits; long ld_logits;   // [nb][V]
     const int* tokens;                 // [nb][DEC_TOK_LD]
     DecodeState* st;
     DecodeSpec spec;
     int nb, k;                         // k = nb + 1 candidates per beam (1 for greedy)
-    float* cand_lp; int* cand_tok;     // [nb][k]
+    SamplePartials* part;
+    float* cand_lp; int* cand_tok;     // [nb][k] (written by the update kernel; kept for decoder1StepFused)
 };
-void sample_topk(const SampleArgs& a, cudaStream_t s);
+void sample_partial(const SampleArgs& a, cudaStream_t s);
 
+// Phase 2 (one CTA): merge the partials into log-softmax + top-k per beam, then GreedyDecoder.update /
+// BeamSearchDecoder.update.  `update` = 0 stops after the candidates (decoder1StepFused).
 struct BeamUpdateArgs {
-    const float* cand_lp; const int* cand_tok; int nb, k;
+    const SamplePartials* part; int timestamp_begin; int update;
+    float* cand_lp; int* cand_tok; int nb, k;
     int* tokens;                       // [nb][DEC_TOK_LD], permuted + extended in place
     int* table;                        // [nb][448] KV slot table, permuted in place
     int* fin_tokens;                   // [DEC_MAX_BEAMS][DEC_TOK_LD]
