@@ -2,6 +2,9 @@
 // (coreml/coreml.h:5-31, bodies coreml/coreml.mm) re-implemented on sm_100a.
 #include <string.h>
 
+#include <stdlib.h>
+
+#include "decoder_mega.cuh"
 #include "decoder_step.cuh"
 #include "gemm.cuh"
 #include "ops.cuh"
@@ -11,6 +14,7 @@
 namespace b200 {
 
 int take_errors(char*, int);
+bool run_step_mega(int nb, int text_offset, const float* d_mask, const float* d_x_in, const MegaArgs* decode_fields);
 void gemm_clear_map_cache();
 void attention_clear_map_cache();
 void decode_clear_graphs();
@@ -113,6 +117,7 @@ void run_cross_kv(int W) {
     State& s = S();
     if (W > s.ckv_cap) {
         if (!dev_alloc(&s.ckv, (size_t)W * s.ckv_window_elems())) return;
+        if (!dev_alloc(&s.ckv_frag, (size_t)W * s.ckv_frag_window_elems(), true)) return;   // pad keys 1500..1503 stay zero
         s.ckv_cap = W;
         gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
     }
@@ -123,6 +128,7 @@ void run_cross_kv(int W) {
     p.B = s.ckv_wt; p.ldb = d; p.N = 2 * s.Ld * d; p.K = d; p.bias = s.ckv_b;
     p.C = s.ckv; p.c_fp32 = 0; p.ldc = 64; p.c_split = 1; p.c_split_stride = (long)N_AUDIO_CTX * 64;
     p.c_batch_rows = 2 * s.Ld * s.H * N_AUDIO_CTX; p.c_row0 = 0; p.add_rows = 1;
+    p.C2 = s.ckv_frag; p.c2_batch_stride = (long)s.ckv_frag_window_elems(); p.c2_heads = s.H; p.c2_keys = CROSS_KEYS_PAD;
     gemm_tcgen05(p, s.stream);
 }
 
@@ -251,6 +257,61 @@ void run_step(int nb, int t, const float* d_mask, bool want_logits, const int* d
 }
 
 // =================================================================================================
+// persistent step kernel: model descriptor + launch
+// =================================================================================================
+static void build_mega_model() {
+    State& s = S();
+    if (!s.dec1_loaded || !s.dec256_loaded || !s.mkv) return;
+    if (s.Ld > MEGA_MAX_LAYERS) return;
+    MegaModel m{};
+    m.d = s.d; m.H = s.H; m.Ld = s.Ld; m.V = s.V; m.n_tiles_vocab = (s.V + 15) / 16;
+    m.tok_emb = s.tok_emb; m.tok_emb_frag = s.tok_emb_frag; m.pos_emb = s.pos_emb; m.ln_w = s.ln_w; m.ln_b = s.ln_b;
+    for (int l = 0; l < s.Ld; ++l) {
+        const DecLayer& L = s.dec_layers[l];
+        MegaLayer& o = m.layers[l];
+        o.qkv = L.qkv.frag; o.attn_out = L.attn_out.frag; o.cross_q = L.cross_q.frag; o.cross_out = L.cross_out.frag;
+        o.mlp1 = L.mlp1.frag; o.mlp2 = L.mlp2.frag;
+        o.qkv_b = L.qkv.b; o.attn_out_b = L.attn_out.b; o.cross_q_b = L.cross_q.b; o.cross_out_b = L.cross_out.b;
+        o.mlp1_b = L.mlp1.b; o.mlp2_b = L.mlp2.b;
+        o.ln1_w = L.attn_ln_w; o.ln1_b = L.attn_ln_b; o.ln2_w = L.cross_ln_w; o.ln2_b = L.cross_ln_b; o.ln3_w = L.mlp_ln_w; o.ln3_b = L.mlp_ln_b;
+        o.cache_k = s.mk_ptr(l); o.cache_v = s.mv_ptr(l);
+    }
+    if (!s.mega_model && cudaMalloc(&s.mega_model, sizeof(MegaModel)) != cudaSuccess) { cudaGetLastError(); s.mega_model = nullptr; return; }
+    B200_CHECK(cudaMemcpy(s.mega_model, &m, sizeof(MegaModel), cudaMemcpyHostToDevice));
+}
+
+bool mega_available() {
+    State& s = S();
+    if (s.step_impl < 0) {
+        const char* e = getenv("B200_STEP_IMPL");
+        s.step_impl = (e && (!strcmp(e, "mega") || !strcmp(e, "0"))) ? 0 : 1;   // default: one kernel per stage (faster today)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&s.n_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int n_splits = (CROSS_KEYS_PAD / 16 + 13) / 14;
+    return s.step_impl == 0 && s.mega_model && s.d % 128 == 0 && s.d <= 1536 && s.Ld <= MEGA_MAX_LAYERS && (s.n_sms % 2) == 0 &&
+           s.H * n_splits <= s.n_sms;
+}
+
+// One token step in one launch.  dc == nullptr: reference ABI semantics (x from the host, logits out, no sampling).
+bool run_step_mega(int nb, int text_offset, const float* d_mask, const float* d_x_in, const MegaArgs* decode_fields) {
+    State& s = S();
+    MegaArgs a{};
+    if (decode_fields) a = *decode_fields;
+    a.model = (const MegaModel*)s.mega_model;
+    a.ckv_frag = s.ckv_frag + (size_t)s.cur_window * s.ckv_frag_window_elems();
+    a.nb = nb; a.xs_cols = std::max(2 * s.d, 224);
+    static int n_slots = 0;
+    if (!n_slots) { const char* e = getenv("B200_MEGA_SLOTS"); n_slots = e ? atoi(e) : 20; if (n_slots < 2 || n_slots > 20) n_slots = 20; }
+    a.n_slots = n_slots;
+    a.xb[0] = s.sx; a.xb[1] = s.sx1; a.part_qkv = s.sqkv; a.part_q = s.sq; a.attn = s.satt; a.hid = s.shid; a.part_m2 = s.spart_m2;
+    a.logits = s.slogits; a.ld_logits = s.V; a.ca_part = s.spart; a.ca_counters = s.scounters; a.table = s.table;
+    a.mask = d_mask; a.x_in = d_x_in; a.text_offset = text_offset; a.barrier = s.mega_barrier; a.dbg = s.mega_dbg;
+    return mega_launch(a, s.n_sms, s.stream);
+}
+
+// =================================================================================================
 // load / close helpers
 // =================================================================================================
 static bool check_dims(const WeightFile& w, int idx, int expect, const char* what) {
@@ -376,7 +437,7 @@ void loadCrossKV(const char* modelPath, int n_layer, int n_state) {
     s.d = n_state; s.H = n_state / 64; s.Ld = n_layer;                  // n_head recomputed (coreml.mm:139)
     s.ckv_wt = s.ckv_w.b16("ckv.w"); s.ckv_b = s.ckv_w.f32("ckv.b");
     s.ckv_cap = 0;
-    if (!dev_alloc(&s.ckv, s.ckv_window_elems())) return;
+    if (!dev_alloc(&s.ckv, s.ckv_window_elems()) || !dev_alloc(&s.ckv_frag, s.ckv_frag_window_elems(), true)) return;
     s.ckv_cap = 1;
     s.ckv_loaded = true;
 }
@@ -386,7 +447,7 @@ void closeCrossKV() {
     if (!s.ckv_loaded) return;
     use_device();
     B200_CHECK(cudaDeviceSynchronize());
-    dev_free(&s.ckv); s.ckv_cap = 0; s.ckv_w.unload(); s.ckv_loaded = false;
+    dev_free(&s.ckv); dev_free(&s.ckv_frag); s.ckv_cap = 0; s.ckv_w.unload(); s.ckv_loaded = false;
     gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
 }
 
@@ -418,6 +479,7 @@ void loadDecoder256(const char* modelPath, int n_layer, int n_state, int n_head,
     build_dump_slots();
     if (!ok) return;
     s.dec256_loaded = true;
+    build_mega_model();
 }
 
 void closeDecoder256() {
@@ -428,6 +490,7 @@ void closeDecoder256() {
     dev_free(&s.mkv); dev_free(&s.table); dev_free(&s.px); dev_free(&s.pout); dev_free(&s.pmask); dev_free(&s.pchw);
     dev_free(&s.py); dev_free(&s.pqkv); dev_free(&s.patt); dev_free(&s.phid); dev_free(&s.pq); dev_free(&s.d_dump_slot);
     release_decoder_weights();
+    if (s.mega_model) { cudaFree(s.mega_model); s.mega_model = nullptr; }
     s.dec256_loaded = false;
     gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
 }
@@ -462,8 +525,11 @@ void loadDecoder1(const char* modelPath, int n_layer, int n_state, int n_head, i
     ok &= dev_alloc(&s.slogits, B * (size_t)s.V); ok &= dev_alloc(&s.smask, (size_t)512);
     ok &= dev_alloc(&s.spart, (size_t)s.H * 8 * 8 * 66); ok &= dev_alloc(&s.scounters, (size_t)s.H, true);
     ok &= dev_alloc(&s.satt, B * d); ok &= dev_alloc(&s.shid, B * 4 * d);
+    ok &= dev_alloc(&s.sx1, B * d); ok &= dev_alloc(&s.sxin, B * d); ok &= dev_alloc(&s.spart_m2, 2 * B * d);
+    ok &= dev_alloc(&s.mega_barrier, (size_t)2, true);
     if (!ok) return;
     s.dec1_loaded = true;
+    build_mega_model();
 }
 
 void closeDecoder1() {
@@ -473,6 +539,8 @@ void closeDecoder1() {
     B200_CHECK(cudaDeviceSynchronize());
     dev_free(&s.sx); dev_free(&s.sqkv); dev_free(&s.sq); dev_free(&s.slogits); dev_free(&s.smask); dev_free(&s.spart);
     dev_free(&s.scounters); dev_free(&s.satt); dev_free(&s.shid);
+    dev_free(&s.sx1); dev_free(&s.sxin); dev_free(&s.spart_m2); dev_free(&s.mega_barrier);
+    if (s.mega_model) { cudaFree(s.mega_model); s.mega_model = nullptr; }
     decode_clear_graphs();
     release_decoder_weights();
     s.dec1_loaded = false;
@@ -505,9 +573,11 @@ void decoder1Predict(float* x, float* qk_mask, int text_offset, float* out_x) {
     use_device();
     const size_t d = s.d;
     const int nb = s.bs;
-    B200_CHECK(cudaMemcpyAsync(s.sx, x, nb * d * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+    const bool mega = mega_available();
+    B200_CHECK(cudaMemcpyAsync(mega ? s.sxin : s.sx, x, nb * d * sizeof(float), cudaMemcpyHostToDevice, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.smask, qk_mask, (size_t)(nb == 1 ? 450 : 449) * sizeof(float), cudaMemcpyHostToDevice, s.stream));
-    run_step(nb, text_offset, s.smask, true, nullptr, nullptr);
+    if (mega) run_step_mega(nb, text_offset, s.smask, s.sxin, nullptr);
+    else run_step(nb, text_offset, s.smask, true, nullptr, nullptr);
     B200_CHECK(cudaMemcpyAsync(out_x, s.slogits, (size_t)nb * s.V * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     B200_CHECK(cudaStreamSynchronize(s.stream));
 }

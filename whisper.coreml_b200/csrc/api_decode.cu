@@ -6,6 +6,7 @@
 #include <tuple>
 #include <vector>
 
+#include "decoder_mega.cuh"
 #include "decoder_step.cuh"
 #include "ops.cuh"
 #include "sampling.cuh"
@@ -96,10 +97,19 @@ void decode_clear_graphs() {
     g_step_graphs.clear();
 }
 
+bool run_step_mega(int nb, int text_offset, const float* d_mask, const float* d_x_in, const MegaArgs* decode_fields);
+
 static void launch_sampling(int nb, int k);
 static void one_step(int nb, int k) {
     State& s = S();
     DecodeCtx& c = g_dc;
+    if (mega_available()) {                                            // the whole step, sampling included, in one launch
+        MegaArgs a{};
+        a.k = k; a.tokens = c.tokens; a.st = c.st; a.spec = c.spec; a.sp = c.part; a.cand_lp = c.cand_lp; a.cand_tok = c.cand_tok;
+        a.fin_tokens = c.fin_tokens; a.do_sampling = 1;
+        run_step_mega(nb, 0, nullptr, nullptr, &a);
+        return;
+    }
     step_embed(s.tok_emb, s.pos_emb, c.tokens, DEC_TOK_LD, 0, &c.st->pos, &c.st->done, nb, s.d, s.sx, s.stream);
     run_step(nb, 0, nullptr, true, &c.st->pos, &c.st->done);
     launch_sampling(nb, k);
@@ -241,7 +251,8 @@ int b200DecodeWindow(const int* initial_tokens, int n_initial, int beam_size, in
     {
         StageTimer t(ST_DECODER1);
         if (steps < sample_len) { one_step(nb, k); ++steps; }           // eager once: sets kernel attributes before any capture
-        StepGraph* g = steps < sample_len ? step_graph(nb, k) : nullptr;
+        // the persistent kernel is one (cooperative) launch per step already; graphs serve the multi-kernel path
+        StepGraph* g = (steps < sample_len && !mega_available()) ? step_graph(nb, k) : nullptr;
         while (!done && steps < sample_len) {
             // launches past sample_len / completion are no-ops: every kernel checks DecodeState::done first
             if (g) { B200_CHECK(cudaGraphLaunch(g->exec, st)); g_launch_count += g->launches; }

@@ -90,3 +90,24 @@ extern "C" void b200TestAttention(const void* dQKV, void* dO, int n_tok, int hea
     if (use_simt) attention_simt(a, S().stream); else attention_tc(a, S().stream);
     B200_CHECK(cudaStreamSynchronize(S().stream));
 }
+
+// Stage timeline of the persistent step kernel: enable = 1 allocates/clears the buffer (every following step appends
+// CTA 0's %globaltimer after each grid barrier); enable = 0 copies up to `cap` timestamps (ns) to `out`, returns the count.
+extern "C" int b200TestStepTimeline(int enable, unsigned long long* out, int cap) {
+    State& s = S();
+    use_device();
+    if (enable) {
+        if (!s.mega_dbg && !dev_alloc(&s.mega_dbg, (size_t)2048)) return 0;
+        B200_CHECK(cudaMemset(s.mega_dbg, 0, 2048 * sizeof(unsigned long long)));
+        return 1;
+    }
+    if (!s.mega_dbg) return 0;
+    static unsigned long long h[2048];
+    B200_CHECK(cudaDeviceSynchronize());
+    B200_CHECK(cudaMemcpy(h, s.mega_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    int n = (int)h[0];
+    if (n > cap) n = cap;
+    for (int i = 0; i < n; ++i) out[i] = h[1 + i];
+    dev_free(&s.mega_dbg);
+    return n;
+}

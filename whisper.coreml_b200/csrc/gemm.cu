@@ -35,6 +35,7 @@ struct GemmKernelArgs {
     int c_batch_rows, c_row0;
     int c_split;
     long c_split_stride;
+    bf16* C2; long c2_batch_stride; int c2_heads, c2_keys;
     int vec_ok;                 // output / residual rows are 16-byte aligned: 128-bit epilogue accesses allowed
 };
 
@@ -151,6 +152,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                         }
                     } else {
                         for (int i = 0; i < 32 && n0 + i < g.N; ++i) v[i] += add_row[n0 + i];
+                    }
+                }
+                if (g.C2) {                                  // fragment-major copy of cross K / V^T (see gemm.cuh)
+                    const int grp = n0 >> 6, c0 = n0 & 63, j = t;
+                    bf16* base = g.C2 + (long)b * g.c2_batch_stride + (long)grp * 64 * g.c2_keys;
+                    if (((grp / g.c2_heads) & 1) == 0) {
+                        bf16* dst = base + ((((j >> 4) * 2 + (c0 >> 5)) * 2 + ((j & 15) >> 3)) * 256) + (j & 7) * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            uint4 q;
+                            q.x = pack_bf16(v[i], v[i + 1]); q.y = pack_bf16(v[i + 2], v[i + 3]);
+                            q.z = pack_bf16(v[i + 4], v[i + 5]); q.w = pack_bf16(v[i + 6], v[i + 7]);
+                            *reinterpret_cast<uint4*>(dst + i) = q;
+                        }
+                    } else {
+                        const int n_kc = g.c2_keys >> 5;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int c = c0 + i;
+                            base[((((c >> 4) * n_kc + (j >> 5)) * 2 + ((c & 15) >> 3)) * 256) + ((c & 7) * 4 + ((j & 31) >> 3)) * 8 + (j & 7)] =
+                                __float2bfloat16(v[i]);
+                        }
                     }
                 }
                 // split mode: 64-column groups (heads) are c_split_stride elements apart
@@ -272,6 +295,7 @@ static void launch(const GemmParams& p, cudaStream_t stream) {
     g.N = p.N; g.bias = p.bias; g.gelu = p.gelu; g.add = p.add; g.add_rows = p.add_rows > 0 ? p.add_rows : 1;
     g.ld_add = p.ld_add; g.C = p.C; g.c_fp32 = p.c_fp32; g.ldc = p.ldc; g.c_batch_rows = p.c_batch_rows; g.c_row0 = p.c_row0;
     g.c_split = p.c_split; g.c_split_stride = p.c_split_stride;
+    g.C2 = p.C2; g.c2_batch_stride = p.c2_batch_stride; g.c2_heads = p.c2_heads > 0 ? p.c2_heads : 1; g.c2_keys = p.c2_keys;
     const long c_elem = p.c_fp32 ? 4 : 2;
     g.vec_ok = ((p.ldc * c_elem) % 16 == 0) && (((uintptr_t)p.C) % 16 == 0) && ((p.c_split_stride * c_elem) % 16 == 0) &&
                (!p.add || (((p.ld_add * 4) % 16 == 0) && (((uintptr_t)p.add) % 16 == 0)));

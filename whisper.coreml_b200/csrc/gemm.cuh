@@ -37,6 +37,13 @@ struct GemmParams {
     int c_row0;
     int c_split;                // 1: column n goes to (n / 64) * c_split_stride + (n % 64) (head-major output, ldc = 64)
     long c_split_stride;
+    // optional second bf16 output for the crossKV projection: per 64-column group (layer, k|v, head) a fragment-major
+    // copy for the decoder step kernel - K as [keys/16][2][1 KB] tiles, V transposed as [4][c2_keys/32][1 KB] tiles
+    // (decoder_mega.cu).  Group g is a V group when (g / c2_heads) is odd.  Rows are keys (row index within the batch).
+    bf16* C2;
+    long c2_batch_stride;
+    int c2_heads;
+    int c2_keys;                // padded key count (multiple of 32)
 };
 
 void gemm_tcgen05(const GemmParams& p, cudaStream_t stream);

@@ -1,134 +1,18 @@
-#include "sampling.cuh"
+#include "sampling_dev.cuh"
 
 namespace b200 {
 
 constexpr int SM_THREADS = 1024;
 
-struct Rules {
-    int at_begin, last_ts, penult_ts, last_stamp, lim;
-};
+struct BlockSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 
-__device__ __forceinline__ bool is_masked(int v, const DecodeSpec& sp, const DecodeState& st, const Rules& r) {
-    if (sp.d_suppress[v]) return true;                                              // SuppressTokens (:460-465)
-    if (r.at_begin && st.suppress_blank &&
-        (v == sp.eot || v == sp.blank[0] || v == sp.blank[1] || v == sp.blank[2] || v == sp.blank[3]))
-        return true;                                                                // SuppressBlank (:450-457)
-    if (st.without_timestamps) return false;
-    const int tb = sp.timestamp_begin;                                              // ApplyTimestampRules (:468-523)
-    if (v == sp.no_timestamps) return true;
-    if (r.last_ts) {
-        if (r.penult_ts) { if (v >= tb) return true; }
-        else if (v < sp.eot) return true;
-    }
-    if (r.last_stamp >= 0 && v >= tb && v < r.lim) return true;
-    if (r.at_begin) {
-        if (v < tb) return true;
-        if (st.max_initial_ts >= 0 && v > tb + st.max_initial_ts) return true;
-    }
-    return false;
-}
-
-__device__ __forceinline__ void online_add(float& m, float& s, float x) {
-    if (x == -INFINITY) return;
-    if (x > m) { s = s * __expf(m - x) + 1.f; m = x; }
-    else s += __expf(x - m);
-}
-__device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
-    if (m2 == -INFINITY) return;
-    if (m == -INFINITY) { m = m2; s = s2; return; }
-    const float M = fmaxf(m, m2);
-    s = s * __expf(m - M) + s2 * __expf(m2 - M);
-    m = M;
-}
-
-constexpr int SP_THREADS = 256, SP_PER_THREAD = 8;     // 256 * 8 = 2048 >= largest chunk (1799 text / 1502 timestamp tokens)
-
-__global__ void __launch_bounds__(SP_THREADS) sample_partial_kernel(const SampleArgs a) {
-    __shared__ Rules rules;
-    __shared__ int s_last;
-    __shared__ float red_m[8], red_s[8];
-    __shared__ float arg_v[8]; __shared__ int arg_i[8]; __shared__ int s_pick;
-    const DecodeState& st = *a.st;
-    if (st.done) return;
-    const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const DecodeSpec& sp = a.spec;
-    const int V = sp.n_vocab, tb = sp.timestamp_begin;
-    const int* seq = a.tokens + b * DEC_TOK_LD + st.sample_begin;
-    const int n = st.L - st.sample_begin;
-    if (tid == 0) s_last = -1;
-    __syncthreads();
-    int last = -1;
-    for (int j = tid; j < n; j += SP_THREADS) if (seq[j] >= tb) last = j;      // position of the last timestamp token
-    last = max(last, __shfl_xor_sync(0xffffffffu, last, 16)); last = max(last, __shfl_xor_sync(0xffffffffu, last, 8));
-    last = max(last, __shfl_xor_sync(0xffffffffu, last, 4)); last = max(last, __shfl_xor_sync(0xffffffffu, last, 2));
-    last = max(last, __shfl_xor_sync(0xffffffffu, last, 1));
-    if (lane == 0 && last >= 0) atomicMax(&s_last, last);
-    __syncthreads();
-    if (tid == 0) {
-        Rules r;
-        r.at_begin = n == 0;
-        r.last_ts = n >= 1 && seq[n - 1] >= tb;
-        r.penult_ts = n < 2 || seq[n - 2] >= tb;
-        r.last_stamp = s_last >= 0 ? seq[s_last] : -1;
-        r.lim = (r.last_ts && !r.penult_ts) ? r.last_stamp : r.last_stamp + 1;
-        rules = r;
-    }
-    __syncthreads();
-    const Rules r = rules;
-    int lo, hi;
-    if (chunk < SAMPLE_TEXT_CHUNKS) {
-        const int per = (tb + SAMPLE_TEXT_CHUNKS - 1) / SAMPLE_TEXT_CHUNKS;
-        lo = chunk * per; hi = min(tb, lo + per);
-    } else { lo = tb; hi = V; }
-    const float* x = a.logits + (long)b * a.ld_logits;
-    float val[SP_PER_THREAD];
-    float m = -INFINITY, s = 0.f;
-#pragma unroll
-    for (int e = 0; e < SP_PER_THREAD; ++e) {
-        const int v = lo + e * SP_THREADS + tid;
-        float t = -INFINITY;
-        if (v < hi && !is_masked(v, sp, st, r)) t = x[v];
-        val[e] = t;
-        online_add(m, s, t);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) online_merge(m, s, __shfl_xor_sync(0xffffffffu, m, o), __shfl_xor_sync(0xffffffffu, s, o));
-    if (lane == 0) { red_m[warp] = m; red_s[warp] = s; }
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < 8; ++w) online_merge(m, s, red_m[w], red_s[w]);
-        a.part->m[b][chunk] = m; a.part->s[b][chunk] = s;
-    }
-    // chunk-local top-k by repeated block arg-max over the register-resident values (ties -> lowest index)
-    unsigned taken = 0;
-    for (int c = 0; c < a.k; ++c) {
-        float bv = -INFINITY; int bi = 0x7fffffff;
-#pragma unroll
-        for (int e = 0; e < SP_PER_THREAD; ++e) {
-            const int v = lo + e * SP_THREADS + tid;
-            if (v < hi && !((taken >> e) & 1u) && (val[e] > bv || (val[e] == bv && v < bi))) { bv = val[e]; bi = v; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (lane == 0) { arg_v[warp] = bv; arg_i[warp] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < 8; ++w) if (arg_v[w] > bv || (arg_v[w] == bv && arg_i[w] < bi)) { bv = arg_v[w]; bi = arg_i[w]; }
-            a.part->topv[b][chunk][c] = bv; a.part->topi[b][chunk][c] = bi;
-            s_pick = bi;
-        }
-        __syncthreads();
-        const int pick = s_pick;                           // a picked slot never competes again
-        if (pick != 0x7fffffff && (pick - lo) % SP_THREADS == tid) taken |= 1u << ((pick - lo) / SP_THREADS);
-    }
+__global__ void __launch_bounds__(256) sample_partial_kernel(const SampleArgs a) {
+    sample_partial_body(a, blockIdx.x, blockIdx.y, threadIdx.x, BlockSync());
 }
 
 void sample_partial(const SampleArgs& a, cudaStream_t s) {
     dim3 grid(SAMPLE_CHUNKS, a.nb);
-    sample_partial_kernel<<<grid, SP_THREADS, 0, s>>>(a);
+    sample_partial_kernel<<<grid, 256, 0, s>>>(a);
     B200_LAUNCH_CHECK();
 }
 
@@ -137,126 +21,7 @@ void sample_partial(const SampleArgs& a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) beam_update_kernel(const BeamUpdateArgs a) {
     __shared__ int stage[DEC_MAX_BEAMS * DEC_TOK_LD];
-    __shared__ int nsrc[DEC_MAX_BEAMS], ntok[DEC_MAX_BEAMS];
-    __shared__ float nsum[DEC_MAX_BEAMS];
-    __shared__ int fin_src[DEC_MAX_BEAMS]; __shared__ float fin_sc[DEC_MAX_BEAMS];
-    __shared__ int s_nfin_new, s_done;
-    __shared__ float c_lp[DEC_MAX_BEAMS * SAMPLE_MAX_K]; __shared__ int c_tok[DEC_MAX_BEAMS * SAMPLE_MAX_K];
-    DecodeState& st = *a.st;
-    if (st.done) return;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nb = a.nb, L = st.L;
-    // ---- warp b: log-softmax normaliser and top-k of beam b from the chunk partials ----------------------
-    if (warp < nb) {
-        const SamplePartials& P = *a.part;
-        float m = -INFINITY, s = 0.f;
-        if (lane < SAMPLE_CHUNKS) { m = P.m[warp][lane]; s = P.s[warp][lane]; }
-        float mt = lane < SAMPLE_TEXT_CHUNKS ? m : -INFINITY, stx = lane < SAMPLE_TEXT_CHUNKS ? s : 0.f;   // text group
-        float mq = lane == SAMPLE_TEXT_CHUNKS ? m : -INFINITY, sq = lane == SAMPLE_TEXT_CHUNKS ? s : 0.f;  // timestamp group
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            online_merge(mt, stx, __shfl_xor_sync(0xffffffffu, mt, o), __shfl_xor_sync(0xffffffffu, stx, o));
-            online_merge(mq, sq, __shfl_xor_sync(0xffffffffu, mq, o), __shfl_xor_sync(0xffffffffu, sq, o));
-        }
-        const float lse_q = mq == -INFINITY ? -INFINITY : mq + logf(sq);
-        float ma = mt, sa = stx;
-        online_merge(ma, sa, mq, sq);
-        const float lse_all = ma == -INFINITY ? -INFINITY : ma + logf(sa);
-        // "if sum of probability over timestamps is above any other token, sample timestamp" (decoding.py:525-532)
-        const bool mask_text = !st.without_timestamps && (lse_q - lse_all) > (mt - lse_all);
-        const float lse = mask_text ? lse_q : lse_all;
-        // candidates: chunk c, rank r -> flat index c * k + r, spread over the lanes
-        const int ncand = SAMPLE_CHUNKS * a.k;
-        unsigned taken = 0;
-        for (int c = 0; c < a.k; ++c) {
-            float bv = -INFINITY; int bi = 0x7fffffff;
-            for (int q = lane, e = 0; q < ncand; q += 32, ++e) {
-                const int ch = q / a.k, rk = q % a.k;
-                if ((taken >> e) & 1u) continue;
-                if (mask_text && ch < SAMPLE_TEXT_CHUNKS) continue;
-                const float v = P.topv[warp][ch][rk]; const int ix = P.topi[warp][ch][rk];
-                if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            for (int q = lane, e = 0; q < ncand; q += 32, ++e)
-                if (P.topi[warp][q / a.k][q % a.k] == bi && !(mask_text && q / a.k < SAMPLE_TEXT_CHUNKS)) taken |= 1u << e;
-            if (lane == 0) {
-                c_lp[warp * a.k + c] = bv - lse; c_tok[warp * a.k + c] = bi;
-                a.cand_lp[warp * a.k + c] = bv - lse; a.cand_tok[warp * a.k + c] = bi;
-            }
-        }
-    }
-    __syncthreads();
-    if (!a.update) return;
-    if (tid == 0) {
-        int nfin_new = 0, done = 0;
-        if (!st.beam_mode) {
-            const int tok = c_tok[0], last = a.tokens[L - 1];
-            nsrc[0] = 0;
-            ntok[0] = last == a.eot ? a.eot : tok;
-            nsum[0] = st.sum_lp[0] + (last == a.eot ? 0.f : c_lp[0]);
-            done = ntok[0] == a.eot;
-        } else {
-            const int nsb = st.step == 0 ? 1 : nb;      // identical prefixes at step 0 collapse to one key set (:366-373)
-            const int n = nsb * a.k;
-            float sc[DEC_MAX_BEAMS * SAMPLE_MAX_K]; int id[DEC_MAX_BEAMS * SAMPLE_MAX_K];
-            for (int j = 0; j < nsb; ++j)
-                for (int c = 0; c < a.k; ++c) { sc[j * a.k + c] = st.sum_lp[j] + c_lp[j * a.k + c]; id[j * a.k + c] = j * a.k + c; }
-            for (int i = 1; i < n; ++i) {                // stable insertion sort, descending (:377)
-                const float s = sc[i]; const int d = id[i];
-                int p = i - 1;
-                while (p >= 0 && sc[p] < s) { sc[p + 1] = sc[p]; id[p + 1] = id[p]; --p; }
-                sc[p + 1] = s; id[p + 1] = d;
-            }
-            int cnt = 0;
-            for (int i = 0; i < n && cnt < nb; ++i) {
-                const int j = id[i] / a.k, tok = c_tok[id[i]];
-                if (tok == a.eot) { if (nfin_new < DEC_MAX_BEAMS) { fin_src[nfin_new] = j; fin_sc[nfin_new] = sc[i]; ++nfin_new; } }
-                else { nsrc[cnt] = j; ntok[cnt] = tok; nsum[cnt] = sc[i]; ++cnt; }
-            }
-            for (; cnt < nb; ++cnt) { nsrc[cnt] = nsrc[cnt > 0 ? cnt - 1 : 0]; ntok[cnt] = ntok[cnt > 0 ? cnt - 1 : 0]; nsum[cnt] = -INFINITY; }
-        }
-        s_nfin_new = nfin_new; s_done = done;
-    }
-    __syncthreads();
-    // finished pool: at most max_candidates (= nb, patience 1) sequences, best first (:396-402)
-    const int max_cand = nb;
-    int nfin = st.n_finished;
-    for (int f = 0; f < s_nfin_new && nfin < max_cand; ++f, ++nfin) {
-        const int* src = a.tokens + fin_src[f] * DEC_TOK_LD;
-        int* dst = a.fin_tokens + nfin * DEC_TOK_LD;
-        for (int i = tid; i < L; i += blockDim.x) dst[i] = src[i];
-        if (tid == 0) { dst[L] = a.eot; st.fin_len[nfin] = L + 1; st.fin_score[nfin] = fin_sc[f]; }
-    }
-    __syncthreads();
-    // permute token histories and KV slot tables by source beam, append the new tokens
-    for (int i = tid; i < nb * DEC_TOK_LD; i += blockDim.x) stage[i] = a.tokens[i];
-    __syncthreads();
-    for (int i = tid; i < nb * L; i += blockDim.x) {
-        const int bb = i / L, p = i % L;
-        a.tokens[bb * DEC_TOK_LD + p] = stage[nsrc[bb] * DEC_TOK_LD + p];
-    }
-    __syncthreads();
-    for (int i = tid; i < nb * 448; i += blockDim.x) stage[i] = a.table[i];
-    __syncthreads();
-    for (int i = tid; i < nb * L; i += blockDim.x) {
-        const int bb = i / L, p = i % L;
-        if (p < 448) a.table[bb * 448 + p] = stage[nsrc[bb] * 448 + p];
-    }
-    if (tid < nb) { a.tokens[tid * DEC_TOK_LD + L] = ntok[tid]; st.sum_lp[tid] = nsum[tid]; }
-    __syncthreads();
-    if (tid == 0) {
-        st.n_finished = nfin;
-        st.L = L + 1; st.pos = L; st.step += 1;
-        int done = s_done;
-        if (st.beam_mode && nfin >= max_cand) done = 1;
-        if (L + 1 > a.n_text_ctx) done = 1;                              // :732
-        if (st.step >= st.sample_len) done = 1;
-        st.done = done;
-    }
+    beam_update_body(a, stage, threadIdx.x, BlockSync());
 }
 
 void beam_update(const BeamUpdateArgs& a, cudaStream_t s) {

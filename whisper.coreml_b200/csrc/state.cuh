@@ -10,6 +10,7 @@
 namespace b200 {
 
 constexpr int N_AUDIO_CTX = 1500, N_FRAMES = 3000, N_TEXT_CTX = 448, PREFILL_CTX = 256;
+constexpr int CROSS_KEYS_PAD = 1504;      // 1500 audio keys padded to a multiple of 32 for the fragment-major copy
 
 struct EncLayer {
     const float *attn_ln_w, *attn_ln_b, *qkv_b, *out_b, *mlp_ln_w, *mlp_ln_b, *mlp1_b, *mlp2_b;
@@ -44,7 +45,8 @@ struct State {
     WeightFile ckv_w;
     int Ld = 0;
     const bf16* ckv_wt = nullptr; const float* ckv_b = nullptr;
-    bf16* ckv = nullptr;              // [w_cap][Ld][2][H][1500][64]
+    bf16* ckv = nullptr;              // [w_cap][Ld][2][H][1500][64]  row-major copy (prefill / alignment attention)
+    bf16* ckv_frag = nullptr;         // [w_cap][Ld][2][H][64 * 1504]  fragment-major copy (decoder step kernel)
     int ckv_cap = 0;
     int cur_window = 0;
 
@@ -66,10 +68,20 @@ struct State {
     float *sx = nullptr, *sqkv = nullptr, *sq = nullptr, *slogits = nullptr, *smask = nullptr, *spart = nullptr;
     bf16 *satt = nullptr, *shid = nullptr;
     int* scounters = nullptr;
+    // persistent step kernel (decoder_mega.cu)
+    void* mega_model = nullptr;       // MegaModel on the device
+    float *sx1 = nullptr, *sxin = nullptr, *spart_m2 = nullptr;
+    unsigned* mega_barrier = nullptr;
+    unsigned long long* mega_dbg = nullptr;   // stage timeline buffer (b200TestStepTimeline)
+    int step_impl = -1;               // -1 undecided, 0 persistent kernel, 1 one kernel per stage (B200_STEP_IMPL=v1)
+    int n_sms = 0;
     float* pin_logits = nullptr;      // pinned host staging
     float* pin_x = nullptr;
 
     size_t ckv_window_elems() const { return (size_t)Ld * 2 * H * N_AUDIO_CTX * 64; }
+    size_t ckv_frag_window_elems() const { return (size_t)Ld * 2 * H * CROSS_KEYS_PAD * 64; }
+    const bf16* ckf_ptr(int w, int l) const { return ckv_frag + w * ckv_frag_window_elems() + (size_t)(l * 2) * H * CROSS_KEYS_PAD * 64; }
+    const bf16* cvf_ptr(int w, int l) const { return ckv_frag + w * ckv_frag_window_elems() + (size_t)(l * 2 + 1) * H * CROSS_KEYS_PAD * 64; }
     bf16* ck_ptr(int w, int l) const { return ckv + w * ckv_window_elems() + (size_t)(l * 2) * H * N_AUDIO_CTX * 64; }
     bf16* cv_ptr(int w, int l) const { return ckv + w * ckv_window_elems() + (size_t)(l * 2 + 1) * H * N_AUDIO_CTX * 64; }
     bf16* mk_ptr(int l) const { return mkv + (size_t)(2 * l) * bs * N_TEXT_CTX * d; }
@@ -107,5 +119,6 @@ void run_cross_kv(int n_windows);
 void run_prefill(int beam_idx, bool want_chw);                            // px/pmask -> pout (+ pchw), KV rows -> slot
 // sx -> slogits; d_t / d_skip: optional device-side text_offset and no-op flag (device-driven decode loop)
 void run_step(int nb, int text_offset, const float* d_mask, bool want_logits, const int* d_t, const int* d_skip);
+bool mega_available();               // persistent step kernel usable for the loaded model?
 
 }  // namespace b200
