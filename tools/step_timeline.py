@@ -16,21 +16,31 @@ m.encode_windows(mel, [0])
 decode(m, DecodingOptions(beam_size=5, sample_len=40), window=0)      # warm
 m.lib.b200TestStepTimeline(1, None, 0)
 decode(m, DecodingOptions(beam_size=5, sample_len=5), window=0)
-buf = np.zeros(2048, dtype=np.uint64)
-n = m.lib.b200TestStepTimeline(0, buf.ctypes.data_as(ctypes.c_void_p), 2048)
-t = buf[:n].astype(np.int64)
-# marks per step: start; per layer: stages 0,2,3,5,6,7 have (prologue, units, barrier)=3 marks, stages 1,4 have (units, barrier)=2
-names = []
-for l in range(dims.n_text_layer):
-    for st, has_pro in (("qkv", 1), ("self_attn", 0), ("out", 1), ("cross_q", 1), ("cross_attn", 0), ("cross_out", 1), ("mlp1", 1), ("mlp2", 1)):
-        if has_pro: names.append(f"L{l}.{st}.prologue")
-        names += [f"L{l}.{st}.units", f"L{l}.{st}.barrier"]
-names += ["vocab.prologue", "vocab.units", "vocab.mark2", "vocab.barrier", "sample.units", "sample.barrier"]
-per = 1 + len(names)
-print("marks", n, "per step", per)
-s0 = 2 * per
-seg = t[s0:s0 + per]
-d = np.diff(seg) / 1000.0
-for k, v in zip(names, d):
-    print(f"{k:28s} {v:8.2f} us")
-print("step total", (seg[-1] - seg[0]) / 1000.0, "us")
+LD = 640
+buf = np.zeros(256 * LD, dtype=np.uint64)
+n = m.lib.b200TestStepTimeline(0, buf.ctypes.data_as(ctypes.c_void_p), 256)
+T = buf[:n * LD].astype(np.int64).reshape(n, LD)
+STAGES = ["qkv", "self_attn", "out_proj", "cross_q", "cross_attn", "cross_out", "mlp1", "mlp2"]
+n_stages = dims.n_text_layer * 8 + 1
+t0 = T[:, 0].min()
+print(f"{n} CTAs; kernel start skew {(T[:, 0].max() - t0) / 1000:.2f} us")
+print(f"{'stage':22s} {'first in':>9s} {'last in':>9s} | {'first ready':>11s} {'last ready':>10s} | {'first done':>10s} {'last done':>9s}   (us since start; in = entered, ready = prologue done)")
+prev_done = T[:, 0]
+for it in range(n_stages):
+    name = f"L{it // 8}.{STAGES[it % 8]}" if it < n_stages - 1 else "vocab"
+    ready, done = T[:, 2 * it + 1], T[:, 2 * it + 2]
+    f = lambda a: (a - t0) / 1000.0
+    print(f"{name:22s} {f(prev_done.min()):9.2f} {f(prev_done.max()):9.2f} | {f(ready.min()):11.2f} {f(ready.max()):10.2f} | {f(done.min()):10.2f} {f(done.max()):9.2f}")
+    prev_done = done
+print("step total", (T[:, 2 * n_stages].max() - t0) / 1000.0, "us")
+names = {1: "sync", 2: "sentinels", 11: "staged+stats", 12: "gamma/beta+sync", 16: "normalised", 17: "sync"}
+for base, nm in ((200, "L0.qkv LN (embed)"), (220, "L0.mlp1 LN (LL)")):
+    c = 100 % n
+    prev = None
+    out = []
+    for k in sorted(names):
+        v = T[c, base + k]
+        if v == 0: continue
+        if prev is not None: out.append(f"{names[k]}+{v - prev}")
+        prev = v
+    print(nm, "CTA", c, "cycles:", " ".join(out))

@@ -278,20 +278,25 @@ static void build_mega_model() {
     }
     if (!s.mega_model && cudaMalloc(&s.mega_model, sizeof(MegaModel)) != cudaSuccess) { cudaGetLastError(); s.mega_model = nullptr; return; }
     B200_CHECK(cudaMemcpy(s.mega_model, &m, sizeof(MegaModel), cudaMemcpyHostToDevice));
+    mega_set_model(m);
 }
+
+// columns of the bf16 activation rows in shared memory: the MLP hidden row (4d) or the 256 cached K | V rows of a self-attention unit (64 KB)
+static int mega_xs_cols(int d) { return std::max(4 * d, 4096); }
 
 bool mega_available() {
     State& s = S();
     if (s.step_impl < 0) {
         const char* e = getenv("B200_STEP_IMPL");
-        s.step_impl = (e && (!strcmp(e, "mega") || !strcmp(e, "0"))) ? 0 : 1;   // default: one kernel per stage (faster today)
+        s.step_impl = (e && (!strcmp(e, "v1") || !strcmp(e, "1"))) ? 1 : 0;     // default: the persistent kernel; v1 = one kernel per stage
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&s.n_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&s.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     }
-    const int n_splits = (CROSS_KEYS_PAD / 16 + 13) / 14;
-    return s.step_impl == 0 && s.mega_model && s.d % 128 == 0 && s.d <= 1536 && s.Ld <= MEGA_MAX_LAYERS && (s.n_sms % 2) == 0 &&
-           s.H * n_splits <= s.n_sms;
+    return s.step_impl == 0 && s.mega_model && s.mega_ll && s.d % 64 == 0 && s.d <= 1280 && s.Ld <= MEGA_MAX_LAYERS &&
+           mega_smem_bytes(mega_xs_cols(s.d), STEP_MAX_BEAMS) <= (size_t)s.smem_optin &&
+           mega_smem_bytes(mega_xs_cols(s.d), 5) <= (size_t)s.smem_optin;
 }
 
 // One token step in one launch.  dc == nullptr: reference ABI semantics (x from the host, logits out, no sampling).
@@ -299,16 +304,23 @@ bool run_step_mega(int nb, int text_offset, const float* d_mask, const float* d_
     State& s = S();
     MegaArgs a{};
     if (decode_fields) a = *decode_fields;
-    a.model = (const MegaModel*)s.mega_model;
     a.ckv_frag = s.ckv_frag + (size_t)s.cur_window * s.ckv_frag_window_elems();
-    a.nb = nb; a.xs_cols = std::max(2 * s.d, 224);
-    static int n_slots = 0;
-    if (!n_slots) { const char* e = getenv("B200_MEGA_SLOTS"); n_slots = e ? atoi(e) : 20; if (n_slots < 2 || n_slots > 20) n_slots = 20; }
-    a.n_slots = n_slots;
-    a.xb[0] = s.sx; a.xb[1] = s.sx1; a.part_qkv = s.sqkv; a.part_q = s.sq; a.attn = s.satt; a.hid = s.shid; a.part_m2 = s.spart_m2;
-    a.logits = s.slogits; a.ld_logits = s.V; a.ca_part = s.spart; a.ca_counters = s.scounters; a.table = s.table;
-    a.mask = d_mask; a.x_in = d_x_in; a.text_offset = text_offset; a.barrier = s.mega_barrier; a.dbg = s.mega_dbg;
+    a.nb = nb; a.xs_cols = mega_xs_cols(s.d); a.xs_rows = mega_xs_rows(nb); a.ring_offset = (int)mega_ring_offset(a.xs_cols, nb);
+    { static const char* e = getenv("B200_MEGA_DELAY"); a.dbg_delay = e ? atoll(e) : 0; }
+    a.n_slots = mega_slots(nb); a.sa_cap = mega_sa_cap(a.xs_cols, nb);
+    { static const char* e = getenv("B200_MEGA_SLOTS"); if (e && atoi(e) >= 2 && atoi(e) < a.n_slots) a.n_slots = atoi(e); }
+    const size_t d = s.d, B = STEP_MAX_BEAMS;
+    uint2* p = s.mega_ll;                                               // carved in the order of mega_ll_words()
+    a.ll_qkv = p; p += B * 3 * d; a.ll_att = p; p += B * d / 2; a.ll_catt = p; p += B * d / 2;
+    a.ll_x1 = p; p += B * d; a.ll_x2 = p; p += B * d; a.ll_x3 = p; p += B * d; a.ll_q = p; p += B * d;
+    a.ll_cap = p; p += (size_t)s.H * 7 * 8 * 66; a.ll_hid = p;
+    a.logits = s.slogits; a.ld_logits = s.V; a.table = s.table;
+    a.mask = d_mask; a.x_in = d_x_in; a.text_offset = text_offset; a.barrier = s.mega_barrier; a.seq = s.mega_barrier + 2; a.dbg = s.mega_dbg;
     return mega_launch(a, s.n_sms, s.stream);
+}
+static size_t mega_ll_words(size_t d, size_t H) {
+    const size_t B = STEP_MAX_BEAMS;
+    return B * 3 * d + 2 * (B * d / 2) + 4 * B * d + H * 7 * 8 * 66 + B * 2 * d;
 }
 
 // =================================================================================================
@@ -525,8 +537,10 @@ void loadDecoder1(const char* modelPath, int n_layer, int n_state, int n_head, i
     ok &= dev_alloc(&s.slogits, B * (size_t)s.V); ok &= dev_alloc(&s.smask, (size_t)512);
     ok &= dev_alloc(&s.spart, (size_t)s.H * 8 * 8 * 66); ok &= dev_alloc(&s.scounters, (size_t)s.H, true);
     ok &= dev_alloc(&s.satt, B * d); ok &= dev_alloc(&s.shid, B * 4 * d);
-    ok &= dev_alloc(&s.sx1, B * d); ok &= dev_alloc(&s.sxin, B * d); ok &= dev_alloc(&s.spart_m2, 2 * B * d);
-    ok &= dev_alloc(&s.mega_barrier, (size_t)2, true);
+    ok &= dev_alloc(&s.sxin, B * d);
+    ok &= dev_alloc(&s.mega_ll, mega_ll_words(d, s.H), true);
+    ok &= dev_alloc(&s.mega_barrier, (size_t)4, true);
+    if (ok) { const unsigned one = 1; B200_CHECK(cudaMemcpy(s.mega_barrier + 2, &one, sizeof(one), cudaMemcpyHostToDevice)); }   // launch sequence starts at 1: epoch 0 = "never written"
     if (!ok) return;
     s.dec1_loaded = true;
     build_mega_model();
@@ -539,7 +553,7 @@ void closeDecoder1() {
     B200_CHECK(cudaDeviceSynchronize());
     dev_free(&s.sx); dev_free(&s.sqkv); dev_free(&s.sq); dev_free(&s.slogits); dev_free(&s.smask); dev_free(&s.spart);
     dev_free(&s.scounters); dev_free(&s.satt); dev_free(&s.shid);
-    dev_free(&s.sx1); dev_free(&s.sxin); dev_free(&s.spart_m2); dev_free(&s.mega_barrier);
+    dev_free(&s.sxin); dev_free(&s.mega_ll); dev_free(&s.mega_barrier);
     if (s.mega_model) { cudaFree(s.mega_model); s.mega_model = nullptr; }
     decode_clear_graphs();
     release_decoder_weights();

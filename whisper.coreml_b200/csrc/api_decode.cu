@@ -103,11 +103,11 @@ static void launch_sampling(int nb, int k);
 static void one_step(int nb, int k) {
     State& s = S();
     DecodeCtx& c = g_dc;
-    if (mega_available()) {                                            // the whole step, sampling included, in one launch
+    if (mega_available()) {                                            // embedding .. logits in one persistent launch
         MegaArgs a{};
-        a.k = k; a.tokens = c.tokens; a.st = c.st; a.spec = c.spec; a.sp = c.part; a.cand_lp = c.cand_lp; a.cand_tok = c.cand_tok;
-        a.fin_tokens = c.fin_tokens; a.do_sampling = 1;
+        a.tokens = c.tokens; a.d_pos = &c.st->pos; a.d_done = &c.st->done;
         run_step_mega(nb, 0, nullptr, nullptr, &a);
+        launch_sampling(nb, k);
         return;
     }
     step_embed(s.tok_emb, s.pos_emb, c.tokens, DEC_TOK_LD, 0, &c.st->pos, &c.st->done, nb, s.d, s.sx, s.stream);
@@ -251,8 +251,7 @@ int b200DecodeWindow(const int* initial_tokens, int n_initial, int beam_size, in
     {
         StageTimer t(ST_DECODER1);
         if (steps < sample_len) { one_step(nb, k); ++steps; }           // eager once: sets kernel attributes before any capture
-        // the persistent kernel is one (cooperative) launch per step already; graphs serve the multi-kernel path
-        StepGraph* g = (steps < sample_len && !mega_available()) ? step_graph(nb, k) : nullptr;
+        StepGraph* g = steps < sample_len ? step_graph(nb, k) : nullptr;
         while (!done && steps < sample_len) {
             // launches past sample_len / completion are no-ops: every kernel checks DecodeState::done first
             if (g) { B200_CHECK(cudaGraphLaunch(g->exec, st)); g_launch_count += g->launches; }

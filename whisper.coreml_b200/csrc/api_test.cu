@@ -1,4 +1,6 @@
 // Test hooks exported through the C ABI (tests/ only; see include/whisper_b200.h).
+#include <algorithm>
+#include "decoder_mega.cuh"
 #include "gemm.cuh"
 #include "ops.cuh"
 #include "whisper_b200.h"
@@ -91,23 +93,23 @@ extern "C" void b200TestAttention(const void* dQKV, void* dO, int n_tok, int hea
     B200_CHECK(cudaStreamSynchronize(S().stream));
 }
 
-// Stage timeline of the persistent step kernel: enable = 1 allocates/clears the buffer (every following step appends
-// CTA 0's %globaltimer after each grid barrier); enable = 0 copies up to `cap` timestamps (ns) to `out`, returns the count.
-extern "C" int b200TestStepTimeline(int enable, unsigned long long* out, int cap) {
+// Stage timeline of the persistent step kernel: enable = 1 allocates/clears the buffer (every following step overwrites
+// it: mark k of CTA c = %globaltimer ns at out[c * MEGA_DBG_LD + k]; mark 0 = start, 2i+1 / 2i+2 = after the prologue /
+// body of stage i); enable = 0 copies the last step's marks of up to `cap_ctas` CTAs to `out` and returns the CTA count.
+extern "C" int b200TestStepTimeline(int enable, unsigned long long* out, int cap_ctas) {
     State& s = S();
     use_device();
+    mega_available();
+    const size_t n = (size_t)s.n_sms * MEGA_DBG_LD;
     if (enable) {
-        if (!s.mega_dbg && !dev_alloc(&s.mega_dbg, (size_t)2048)) return 0;
-        B200_CHECK(cudaMemset(s.mega_dbg, 0, 2048 * sizeof(unsigned long long)));
+        if (!s.mega_dbg && !dev_alloc(&s.mega_dbg, n)) return 0;
+        B200_CHECK(cudaMemset(s.mega_dbg, 0, n * sizeof(unsigned long long)));
         return 1;
     }
     if (!s.mega_dbg) return 0;
-    static unsigned long long h[2048];
     B200_CHECK(cudaDeviceSynchronize());
-    B200_CHECK(cudaMemcpy(h, s.mega_dbg, sizeof(h), cudaMemcpyDeviceToHost));
-    int n = (int)h[0];
-    if (n > cap) n = cap;
-    for (int i = 0; i < n; ++i) out[i] = h[1 + i];
+    const int n_ctas = std::min(cap_ctas, s.n_sms);
+    B200_CHECK(cudaMemcpy(out, s.mega_dbg, (size_t)n_ctas * MEGA_DBG_LD * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     dev_free(&s.mega_dbg);
-    return n;
+    return n_ctas;
 }

@@ -70,8 +70,10 @@ struct State {
     int* scounters = nullptr;
     // persistent step kernel (decoder_mega.cu)
     void* mega_model = nullptr;       // MegaModel on the device
-    float *sx1 = nullptr, *sxin = nullptr, *spart_m2 = nullptr;
-    unsigned* mega_barrier = nullptr;
+    float* sxin = nullptr;
+    uint2* mega_ll = nullptr;         // LL activation words (decoder_mega.cuh: MegaArgs::ll_*)
+    unsigned* mega_barrier = nullptr; // [0] arrivals, [1] leavers, [2] launch sequence number
+    int smem_optin = 0;
     unsigned long long* mega_dbg = nullptr;   // stage timeline buffer (b200TestStepTimeline)
     int step_impl = -1;               // -1 undecided, 0 persistent kernel, 1 one kernel per stage (B200_STEP_IMPL=v1)
     int n_sms = 0;
