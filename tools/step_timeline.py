@@ -32,7 +32,15 @@ for it in range(n_stages):
     f = lambda a: (a - t0) / 1000.0
     print(f"{name:22s} {f(prev_done.min()):9.2f} {f(prev_done.max()):9.2f} | {f(ready.min()):11.2f} {f(ready.max()):10.2f} | {f(done.min()):10.2f} {f(done.max()):9.2f}")
     prev_done = done
-print("step total", (T[:, 2 * n_stages].max() - t0) / 1000.0, "us")
+tail = [("barrier", 2 * n_stages + 1), ("sample_partial", 2 * n_stages + 2), ("barrier", 2 * n_stages + 3), ("beam_update (CTA 0)", 2 * n_stages + 4)]
+prev = T[:, 2 * n_stages]
+for nm, k in tail:
+    cur = T[:, k]
+    ok = cur > 0
+    if not ok.any(): break
+    print(f"{nm:22s} {(prev[prev > 0].max() - t0) / 1000:9.2f} -> first {(cur[ok].min() - t0) / 1000:9.2f} last {(cur[ok].max() - t0) / 1000:9.2f}")
+    prev = cur
+print("step total", (T[:, :2 * n_stages + 5].max() - t0) / 1000.0, "us")
 names = {1: "sync", 2: "sentinels", 11: "staged+stats", 12: "gamma/beta+sync", 16: "normalised", 17: "sync"}
 for base, nm in ((200, "L0.qkv LN (embed)"), (220, "L0.mlp1 LN (LL)")):
     c = 100 % n

@@ -1,4 +1,5 @@
 // C ABI Part 2: batched windows and the device-resident decode loop.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -106,8 +107,12 @@ static void one_step(int nb, int k) {
     if (mega_available()) {                                            // embedding .. logits in one persistent launch
         MegaArgs a{};
         a.tokens = c.tokens; a.d_pos = &c.st->pos; a.d_done = &c.st->done;
+        // B200_MEGA_SAMPLING=1 runs the sampling tail inside the kernel too; measured slower (61 us vs ~55 us): with one warp
+        // per scheduler and no L1 the serial beam update is latency bound there, the two stand-alone kernels are not
+        static const bool fused = getenv("B200_MEGA_SAMPLING") && atoi(getenv("B200_MEGA_SAMPLING")) != 0;
+        if (fused) { a.do_sampling = 1; a.k = k; a.st = c.st; a.spec = c.spec; a.sp = c.part; a.cand_lp = c.cand_lp; a.cand_tok = c.cand_tok; a.fin_tokens = c.fin_tokens; }
         run_step_mega(nb, 0, nullptr, nullptr, &a);
-        launch_sampling(nb, k);
+        if (!fused) launch_sampling(nb, k);
         return;
     }
     step_embed(s.tok_emb, s.pos_emb, c.tokens, DEC_TOK_LD, 0, &c.st->pos, &c.st->done, nb, s.d, s.sx, s.stream);

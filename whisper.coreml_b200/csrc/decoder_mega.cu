@@ -33,6 +33,8 @@
 // the same CUDA graph.
 #include "decoder_mega.cuh"
 
+#include "sampling_dev.cuh"
+
 namespace b200 {
 
 constexpr int MG_CONSUMERS = 128, MG_THREADS = 160, MG_CWARPS = 4;
@@ -52,6 +54,7 @@ __device__ __forceinline__ void mg_mma(float (&d)[4], const uint4& lo, const uin
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(lo.z), "r"(hi.z), "r"(lo.w), "r"(hi.w), "r"(xb.z), "r"(xb.w));
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+struct ConsumerSync { __device__ __forceinline__ void operator()() const { consumer_sync(); } };
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -650,6 +653,23 @@ __device__ __forceinline__ void stage_cross_attn(const MegaSmem& sm, Ring& ring,
     }
 }
 
+// ---- grid barrier (consumers only) for the sampling tail: arrivals count monotonically within a launch (barrier k completes at
+// k * nctas); the last CTA to leave the kernel re-arms the word --------------------------------------------------------------
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& k, int nctas, int tid) {
+    consumer_sync();                                   // orders this CTA's stores before thread 0's release (cumulativity)
+    if (tid == 0) {
+        ++k;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        const unsigned target = k * (unsigned)nctas;
+        unsigned spins = 0, v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if (++spins > MG_SPIN_LIMIT) mg_timeout(100 + (int)k);
+        } while (v < target);
+    }
+    consumer_sync();
+}
+
 // ---- the stage table: stage `it` of the step (8 per layer + the vocabulary projection) ----------------------------------------
 enum { ST_QKV = 0, ST_SA, ST_OUT, ST_CQ, ST_CA, ST_CO, ST_M1, ST_M2, ST_VOCAB };
 struct StageDesc {                     // what the producer needs: the weight matrix of a GEMV stage and who owns which tile
@@ -813,10 +833,31 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decoder_mega_kernel(const __gri
         stage_gemv(sm, ring, red_buf, g, a, pos, nctas, warp, lane);
         dbg.mark(2 * it + 2);
     }
-    // the last CTA to leave advances the launch sequence number: by then every CTA has read it
+    if (a.do_sampling) {
+        // ---- tail of the device-resident decode loop: two real grid barriers (every CTA's logits are needed) ----
+        unsigned bar_k = 0;
+        grid_sync(a.barrier, bar_k, nctas, tid);
+        dbg.mark(2 * n_stages + 1);
+        SampleArgs sa;                             // logit filters + partial log-softmax / top-k per (chunk, beam)
+        sa.logits = a.logits; sa.ld_logits = a.ld_logits; sa.tokens = a.tokens; sa.st = a.st; sa.spec = a.spec; sa.nb = a.nb; sa.k = a.k;
+        sa.part = a.sp; sa.cand_lp = a.cand_lp; sa.cand_tok = a.cand_tok;
+        for (int u = cta; u < SAMPLE_CHUNKS * a.nb; u += nctas) sample_partial_body<MG_CONSUMERS>(sa, u % SAMPLE_CHUNKS, u / SAMPLE_CHUNKS, tid, ConsumerSync());
+        dbg.mark(2 * n_stages + 2);
+        grid_sync(a.barrier, bar_k, nctas, tid);
+        dbg.mark(2 * n_stages + 3);
+        if (cta == 0) {                            // merge + greedy / beam update
+            BeamUpdateArgs ba;
+            ba.part = a.sp; ba.timestamp_begin = a.spec.timestamp_begin; ba.update = 1; ba.cand_lp = a.cand_lp; ba.cand_tok = a.cand_tok;
+            ba.nb = a.nb; ba.k = a.k; ba.tokens = a.tokens; ba.table = a.table; ba.fin_tokens = a.fin_tokens; ba.st = a.st;
+            ba.eot = a.spec.eot; ba.n_text_ctx = N_TEXT_CTX;
+            beam_update_body<MG_CONSUMERS>(ba, reinterpret_cast<int*>(sm.xs), tid, ConsumerSync());
+        }
+        dbg.mark(2 * n_stages + 4);
+    }
+    // the last CTA to leave re-arms the barrier and advances the launch sequence number: by then every CTA has read it
     if (tid == 0) {
         const unsigned old = atomicAdd(&a.barrier[1], 1u);
-        if (old == (unsigned)nctas - 1) { a.barrier[1] = 0; *a.seq = seq + 1; }
+        if (old == (unsigned)nctas - 1) { a.barrier[0] = 0; a.barrier[1] = 0; *a.seq = seq + 1; }
     }
 }
 

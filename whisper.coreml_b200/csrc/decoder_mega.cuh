@@ -34,12 +34,14 @@ struct MegaArgs {
     uint2 *ll_cap;                      // [H][7][8][66] fp32 cross-attention partials (max, sum, o[64]) per key split
     uint2 *ll_hid;                      // [8][2d]   bf16x2 MLP hidden activations
     float* logits; long ld_logits;
-    int* table; const int* tokens;      // KV slot table [8][448]; token histories [8][DEC_TOK_LD] (nullptr with x_in)
+    int* table; int* tokens;            // KV slot table [8][448]; token histories [8][DEC_TOK_LD] (nullptr with x_in)
+    // device-resident decode loop (do_sampling): logit filters + top-k + beam update run in the kernel's tail
+    int do_sampling, k; DecodeState* st; DecodeSpec spec; SamplePartials* sp; float* cand_lp; int* cand_tok; int* fin_tokens;
     const int* d_pos; const int* d_done;   // device-resident decode loop: text_offset and completion flag, else nullptr
     const float* mask;                  // reference ABI: additive (449) mask on the device, else nullptr
     const float* x_in;                  // reference ABI: embedded tokens fp32 [nb][d] on the device, else nullptr
     int text_offset;                    // used when d_pos == nullptr
-    unsigned* barrier;                  // [1] CTAs that have left the kernel
+    unsigned* barrier;                  // [0] grid-barrier arrivals, [1] CTAs that have left the kernel
     unsigned* seq;                      // launch sequence number (device memory; the kernel increments it)
     long long dbg_delay;                // experiment: cycles the producer waits before it starts streaming
     unsigned long long* dbg;            // optional stage timeline: [n_ctas][MEGA_DBG_LD] %globaltimer values (0 = not reached)

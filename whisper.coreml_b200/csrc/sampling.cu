@@ -2,12 +2,10 @@
 
 namespace b200 {
 
-constexpr int SM_THREADS = 1024;
-
 struct BlockSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 
 __global__ void __launch_bounds__(256) sample_partial_kernel(const SampleArgs a) {
-    sample_partial_body(a, blockIdx.x, blockIdx.y, threadIdx.x, BlockSync());
+    sample_partial_body<256>(a, blockIdx.x, blockIdx.y, threadIdx.x, BlockSync());
 }
 
 void sample_partial(const SampleArgs& a, cudaStream_t s) {
@@ -21,7 +19,7 @@ void sample_partial(const SampleArgs& a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) beam_update_kernel(const BeamUpdateArgs a) {
     __shared__ int stage[DEC_MAX_BEAMS * DEC_TOK_LD];
-    beam_update_body(a, stage, threadIdx.x, BlockSync());
+    beam_update_body<256>(a, stage, threadIdx.x, BlockSync());
 }
 
 void beam_update(const BeamUpdateArgs& a, cudaStream_t s) {

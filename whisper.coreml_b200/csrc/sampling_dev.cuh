@@ -42,11 +42,13 @@ __device__ __forceinline__ void online_merge(float& m, float& s, float m2, float
     m = M;
 }
 
-constexpr int SP_THREADS = 256, SP_PER_THREAD = 8;     // 256 * 8 = 2048 >= largest chunk (1799 text / 1502 timestamp tokens)
+constexpr int SP_CHUNK_MAX = 2048;                     // >= largest chunk (1799 text / 1502 timestamp tokens)
 
-// One (chunk, beam) unit; `tid` in [0, 256); sync() is a barrier over exactly those 256 threads.
-template <class Sync>
+// One (chunk, beam) unit; `tid` in [0, SP_THREADS); sync() is a barrier over exactly those SP_THREADS threads (256 in the
+// stand-alone kernel, the 128 consumer threads inside the persistent step kernel).
+template <int SP_THREADS, class Sync>
 __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chunk, int b, int tid, Sync sync) {
+    constexpr int SP_PER_THREAD = SP_CHUNK_MAX / SP_THREADS, SP_WARPS = SP_THREADS / 32;
     __shared__ Rules rules;
     __shared__ int s_last;
     __shared__ float red_m[8], red_s[8];
@@ -99,7 +101,7 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
     if (lane == 0) { red_m[warp] = m; red_s[warp] = s; }
     sync();
     if (tid == 0) {
-        for (int w = 1; w < 8; ++w) online_merge(m, s, red_m[w], red_s[w]);
+        for (int w = 1; w < SP_WARPS; ++w) online_merge(m, s, red_m[w], red_s[w]);
         a.part->m[b][chunk] = m; a.part->s[b][chunk] = s;
     }
     // chunk-local top-k by repeated block arg-max over the register-resident values (ties -> lowest index)
@@ -119,7 +121,7 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
         if (lane == 0) { arg_v[warp] = bv; arg_i[warp] = bi; }
         sync();
         if (tid == 0) {
-            for (int w = 1; w < 8; ++w) if (arg_v[w] > bv || (arg_v[w] == bv && arg_i[w] < bi)) { bv = arg_v[w]; bi = arg_i[w]; }
+            for (int w = 1; w < SP_WARPS; ++w) if (arg_v[w] > bv || (arg_v[w] == bv && arg_i[w] < bi)) { bv = arg_v[w]; bi = arg_i[w]; }
             a.part->topv[b][chunk][c] = bv; a.part->topi[b][chunk][c] = bi;
             s_pick = bi;
         }
@@ -130,9 +132,11 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
 }
 
 
-// `stage`: DEC_MAX_BEAMS * DEC_TOK_LD ints of shared scratch; `tid` in [0, 256); sync() as above.
-template <class Sync>
+// `stage`: DEC_MAX_BEAMS * DEC_TOK_LD ints of shared scratch; `tid` in [0, NT); sync() as above.  Nothing here may live in
+// local memory (inside the persistent kernel a stack access is an L2 round trip): the sort keys are in shared memory.
+template <int NT, class Sync>
 __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* stage, int tid, Sync sync) {
+    __shared__ float sc[DEC_MAX_BEAMS * SAMPLE_MAX_K]; __shared__ int id[DEC_MAX_BEAMS * SAMPLE_MAX_K];
     __shared__ int nsrc[DEC_MAX_BEAMS], ntok[DEC_MAX_BEAMS];
     __shared__ float nsum[DEC_MAX_BEAMS];
     __shared__ int fin_src[DEC_MAX_BEAMS]; __shared__ float fin_sc[DEC_MAX_BEAMS];
@@ -142,7 +146,8 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
     if (st.done) return;
     const int warp = tid >> 5, lane = tid & 31, nb = a.nb, L = st.L;
     // ---- warp b: log-softmax normaliser and top-k of beam b from the chunk partials ----------------------
-    if (warp < nb) {
+    for (int bw = warp; bw < nb; bw += NT / 32) {
+        const int warp = bw;                                 // one warp per beam
         const SamplePartials& P = *a.part;
         float m = -INFINITY, s = 0.f;
         if (lane < SAMPLE_CHUNKS) { m = P.m[warp][lane]; s = P.s[warp][lane]; }
@@ -198,7 +203,6 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
         } else {
             const int nsb = st.step == 0 ? 1 : nb;      // identical prefixes at step 0 collapse to one key set (:366-373)
             const int n = nsb * a.k;
-            float sc[DEC_MAX_BEAMS * SAMPLE_MAX_K]; int id[DEC_MAX_BEAMS * SAMPLE_MAX_K];
             for (int j = 0; j < nsb; ++j)
                 for (int c = 0; c < a.k; ++c) { sc[j * a.k + c] = st.sum_lp[j] + c_lp[j * a.k + c]; id[j * a.k + c] = j * a.k + c; }
             for (int i = 1; i < n; ++i) {                // stable insertion sort, descending (:377)
@@ -224,21 +228,21 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
     for (int f = 0; f < s_nfin_new && nfin < max_cand; ++f, ++nfin) {
         const int* src = a.tokens + fin_src[f] * DEC_TOK_LD;
         int* dst = a.fin_tokens + nfin * DEC_TOK_LD;
-        for (int i = tid; i < L; i += 256) dst[i] = src[i];
+        for (int i = tid; i < L; i += NT) dst[i] = src[i];
         if (tid == 0) { dst[L] = a.eot; st.fin_len[nfin] = L + 1; st.fin_score[nfin] = fin_sc[f]; }
     }
     sync();
     // permute token histories and KV slot tables by source beam, append the new tokens
-    for (int i = tid; i < nb * DEC_TOK_LD; i += 256) stage[i] = a.tokens[i];
+    for (int i = tid; i < nb * DEC_TOK_LD; i += NT) stage[i] = a.tokens[i];
     sync();
-    for (int i = tid; i < nb * L; i += 256) {
+    for (int i = tid; i < nb * L; i += NT) {
         const int bb = i / L, p = i % L;
         a.tokens[bb * DEC_TOK_LD + p] = stage[nsrc[bb] * DEC_TOK_LD + p];
     }
     sync();
-    for (int i = tid; i < nb * 448; i += 256) stage[i] = a.table[i];
+    for (int i = tid; i < nb * 448; i += NT) stage[i] = a.table[i];
     sync();
-    for (int i = tid; i < nb * L; i += 256) {
+    for (int i = tid; i < nb * L; i += NT) {
         const int bb = i / L, p = i % L;
         if (p < 448) a.table[bb * 448 + p] = stage[nsrc[bb] * 448 + p];
     }
