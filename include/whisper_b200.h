@@ -118,6 +118,15 @@ void b200SelectWindow(int w);
 int b200DecodeWindow(const int* initial_tokens, int n_initial, int beam_size, int sample_len,
                      int without_timestamps, int max_initial_timestamp_index,
                      int* out_tokens, int* out_lengths, float* out_sum_logprobs, float* out_no_speech);
+/* The same for n_windows encoded windows (ids as for b200SelectWindow).  Independent windows are decoded CONCURRENTLY:
+ * up to 2 decode lanes, each with its own KV cache, decode state and stream, each step kernel on its share of the SMs
+ * (the token loop is latency bound, so two lanes nearly double the throughput; B200_DECODE_LANES=1 disables it).
+ * Outputs are the b200DecodeWindow outputs per window, window-major: out_tokens (n_windows, n_cand, 449), out_lengths and
+ * out_sum_logprobs (n_windows, n_cand), out_no_speech (n_windows), out_steps (n_windows, may be NULL).
+ * Returns the total number of sampling steps.  This is what transcribe() calls (whisper/transcribe.py:276-306 loops windows). */
+int b200DecodeWindows(const int* windows, int n_windows, const int* initial_tokens, int n_initial, int beam_size,
+                      int sample_len, int without_timestamps, int max_initial_timestamp_index, int* out_tokens,
+                      int* out_lengths, float* out_sum_logprobs, float* out_no_speech, int* out_steps);
 
 /* decoder1 with on-device filters + log-softmax + top-(bs+1) instead of returning full logits:
  * tokens_hist (bs, n_hist) int32 HOST = whole context so far (last column is fed to the

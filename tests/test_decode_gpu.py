@@ -86,3 +86,23 @@ def test_alignment(case):
     assert np.array_equal(al.text_indices, oi) and np.array_equal(al.time_indices, oj)
     assert len(al.text_token_probs) == len(text) and np.all(al.text_token_probs >= 0) and np.all(al.text_token_probs <= 1)
     assert len(al.jump_times) == len(text) + 1              # one start time per matrix row (no_timestamps row + text rows)
+
+
+def test_concurrent_windows_match_sequential():
+    """b200DecodeWindows decodes independent windows on concurrent lanes (each on half of the SMs): same tokens as one by one."""
+    from whisper_b200.decoding import DecodingOptions, decode, decode_windows
+    from whisper_b200.model import ModelDimensions, WhisperB200
+    dims, ckpt, folder = exported("tiny", 0, 1.0)
+    m = WhisperB200(ModelDimensions(**dims.as_dict()), folder).load()
+    audio = torch.cat([synth.noise_audio(1, 480000), synth.noise_audio(2, 480000), synth.noise_audio(3, 480000)])
+    mel = oa.log_mel_spectrogram(audio, dims.n_mels, padding=480000)
+    m.encode_windows(mel.cuda(), [0, 3000, 6000])
+    for beam in (5, None):
+        opts = DecodingOptions(sample_len=32, beam_size=beam)
+        one_by_one = [decode(m, opts, window=w) for w in range(3)]
+        together = decode_windows(m, opts, [0, 1, 2])
+        for a, b in zip(one_by_one, together):
+            assert a.tokens == b.tokens, (beam, a.tokens, b.tokens)
+            assert a.steps == b.steps
+            assert abs(a.sum_logprob - b.sum_logprob) <= 1e-3 * max(1.0, abs(a.sum_logprob))
+    m.close()

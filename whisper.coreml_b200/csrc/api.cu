@@ -274,7 +274,6 @@ static void build_mega_model() {
         o.qkv_b = L.qkv.b; o.attn_out_b = L.attn_out.b; o.cross_q_b = L.cross_q.b; o.cross_out_b = L.cross_out.b;
         o.mlp1_b = L.mlp1.b; o.mlp2_b = L.mlp2.b;
         o.ln1_w = L.attn_ln_w; o.ln1_b = L.attn_ln_b; o.ln2_w = L.cross_ln_w; o.ln2_b = L.cross_ln_b; o.ln3_w = L.mlp_ln_w; o.ln3_b = L.mlp_ln_b;
-        o.cache_k = s.mk_ptr(l); o.cache_v = s.mv_ptr(l);
     }
     if (!s.mega_model && cudaMalloc(&s.mega_model, sizeof(MegaModel)) != cudaSuccess) { cudaGetLastError(); s.mega_model = nullptr; return; }
     B200_CHECK(cudaMemcpy(s.mega_model, &m, sizeof(MegaModel), cudaMemcpyHostToDevice));
@@ -314,11 +313,13 @@ bool run_step_mega(int nb, int text_offset, const float* d_mask, const float* d_
     a.ll_qkv = p; p += B * 3 * d; a.ll_att = p; p += B * d / 2; a.ll_catt = p; p += B * d / 2;
     a.ll_x1 = p; p += B * d; a.ll_x2 = p; p += B * d; a.ll_x3 = p; p += B * d; a.ll_q = p; p += B * d;
     a.ll_cap = p; p += (size_t)s.H * 7 * 8 * 66; a.ll_hid = p;
-    a.logits = s.slogits; a.ld_logits = s.V; a.table = s.table;
+    a.logits = s.slogits; a.ld_logits = s.V; a.table = s.table; a.mkv = s.mkv; a.kv_stride = (long)s.bs * N_TEXT_CTX * s.d;
     a.mask = d_mask; a.x_in = d_x_in; a.text_offset = text_offset; a.barrier = s.mega_barrier; a.seq = s.mega_barrier + 2; a.dbg = s.mega_dbg;
-    return mega_launch(a, s.n_sms, s.stream);
+    return mega_launch(a, s.mega_ctas > 0 ? s.mega_ctas : s.n_sms, s.stream);
 }
-static size_t mega_ll_words(size_t d, size_t H) {
+size_t mega_ll_words_for(size_t d, size_t H);
+static size_t mega_ll_words(size_t d, size_t H) { return mega_ll_words_for(d, H); }
+size_t mega_ll_words_for(size_t d, size_t H) {
     const size_t B = STEP_MAX_BEAMS;
     return B * 3 * d + 2 * (B * d / 2) + 4 * B * d + H * 7 * 8 * 66 + B * 2 * d;
 }
@@ -499,6 +500,7 @@ void closeDecoder256() {
     if (!s.dec256_loaded) return;
     use_device();
     B200_CHECK(cudaDeviceSynchronize());
+    decode_free_lanes();
     dev_free(&s.mkv); dev_free(&s.table); dev_free(&s.px); dev_free(&s.pout); dev_free(&s.pmask); dev_free(&s.pchw);
     dev_free(&s.py); dev_free(&s.pqkv); dev_free(&s.patt); dev_free(&s.phid); dev_free(&s.pq); dev_free(&s.d_dump_slot);
     release_decoder_weights();
@@ -551,6 +553,7 @@ void closeDecoder1() {
     if (!s.dec1_loaded) return;
     use_device();
     B200_CHECK(cudaDeviceSynchronize());
+    decode_free_lanes();
     dev_free(&s.sx); dev_free(&s.sqkv); dev_free(&s.sq); dev_free(&s.slogits); dev_free(&s.smask); dev_free(&s.spart);
     dev_free(&s.scounters); dev_free(&s.satt); dev_free(&s.shid);
     dev_free(&s.sxin); dev_free(&s.mega_ll); dev_free(&s.mega_barrier);

@@ -122,7 +122,7 @@ static void one_step(int nb, int k) {
 
 static StepGraph* step_graph(int nb, int k) {
     State& s = S();
-    auto key = std::make_tuple(nb, k, (const void*)s.ck_ptr(s.cur_window, 0), (const void*)s.mkv, (const void*)s.slogits);
+    auto key = std::make_tuple(nb * 1000 + s.mega_ctas, k, (const void*)s.ck_ptr(s.cur_window, 0), (const void*)s.mkv, (const void*)s.slogits);
     auto it = g_step_graphs.find(key);
     if (it != g_step_graphs.end()) return &it->second;
     cudaGraph_t graph = nullptr;
@@ -203,25 +203,86 @@ void crossKVPredictWindows(int n_windows) {
     B200_CHECK(cudaStreamSynchronize(s.stream));
 }
 
-int b200DecodeWindow(const int* initial_tokens, int n_initial, int beam_size, int sample_len, int without_timestamps,
-                     int max_initial_timestamp_index, int* out_tokens, int* out_lengths, float* out_sum_logprobs,
-                     float* out_no_speech) {
+}  // extern "C"
+
+namespace b200 {
+
+// ---- decode lanes --------------------------------------------------------------------------------------------------------
+// The persistent step kernel is latency bound (one token step is a chain of ~38 dependent stages), so independent windows
+// are decoded CONCURRENTLY, each lane on its own stream with its own KV cache / decode state and its share of the SMs
+// (n_sms / lanes CTAs per step kernel).  Lane 0 is the process-global state of the reference ABI; switching lanes swaps
+// the lane-specific pointers of State / DecodeCtx with the parked copy, so every kernel-launching helper stays lane-agnostic.
+struct Lane {
+    cudaStream_t stream = nullptr;
+    bf16* mkv = nullptr; int* table = nullptr; float* slogits = nullptr; uint2* mega_ll = nullptr; unsigned* mega_barrier = nullptr;
+    DecodeState* st = nullptr; int* tokens = nullptr; int* fin_tokens = nullptr; float* cand_lp = nullptr; int* cand_tok = nullptr;
+    SamplePartials* part = nullptr; float* ns_logits = nullptr; int* pin_done = nullptr;
+    int cur_window = 0;
+    bool ready = false;
+};
+static Lane g_parked[MAX_LANES];          // g_parked[i] holds lane i's pointers while another lane is active (entry 0 unused until a swap)
+static int g_active_lane = 0;
+
+static void lane_swap(Lane& l) {
     State& s = S();
     DecodeCtx& c = g_dc;
-    if (!s.dec1_loaded || !s.dec256_loaded || !s.ckv_loaded) { record_error("b200DecodeWindow: decoder256 / decoder1 / crossKV not loaded"); return 0; }
-    const int nb = beam_size > 0 ? beam_size : 1;
-    if (nb > s.bs) { record_error("b200DecodeWindow: %d beams but loadDecoder256 reserved %d cache slots", nb, s.bs); return 0; }
-    if (n_initial < 1 || n_initial > PREFILL_CTX) { record_error("b200DecodeWindow: n_initial %d outside [1, 256]", n_initial); return 0; }
-    if (sample_len < 1) return 0;
-    use_device();
-    if (!ensure_decode_ctx()) return 0;
+    std::swap(l.stream, s.stream); std::swap(l.mkv, s.mkv); std::swap(l.table, s.table); std::swap(l.slogits, s.slogits);
+    std::swap(l.mega_ll, s.mega_ll); std::swap(l.mega_barrier, s.mega_barrier); std::swap(l.cur_window, s.cur_window);
+    std::swap(l.st, c.st); std::swap(l.tokens, c.tokens); std::swap(l.fin_tokens, c.fin_tokens); std::swap(l.cand_lp, c.cand_lp);
+    std::swap(l.cand_tok, c.cand_tok); std::swap(l.part, c.part); std::swap(l.ns_logits, c.ns_logits); std::swap(l.pin_done, c.pin_done);
+}
+static void activate_lane(int i) {
+    if (i == g_active_lane) return;
+    lane_swap(g_parked[g_active_lane]);    // park the active lane ...
+    lane_swap(g_parked[i]);                // ... and bring lane i in
+    g_active_lane = i;
+}
+size_t mega_ll_words_for(size_t d, size_t H);
+static bool ensure_lane(int i) {           // allocate lane i > 0 (the active lane must be 0)
+    Lane& l = g_parked[i];
+    if (l.ready) return true;
+    State& s = S();
+    const size_t d = s.d;
+    bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok &= dev_alloc(&l.mkv, (size_t)2 * s.Ld * s.bs * N_TEXT_CTX * d, true);
+    ok &= dev_alloc(&l.table, (size_t)STEP_MAX_BEAMS * N_TEXT_CTX, true);
+    ok &= dev_alloc(&l.slogits, (size_t)STEP_MAX_BEAMS * s.V);
+    ok &= dev_alloc(&l.mega_ll, mega_ll_words_for(d, s.H), true);
+    ok &= dev_alloc(&l.mega_barrier, (size_t)4, true);
+    if (ok) { const unsigned one = 1; B200_CHECK(cudaMemcpy(l.mega_barrier + 2, &one, sizeof(one), cudaMemcpyHostToDevice)); }
+    ok &= dev_alloc(&l.st, 1, true);
+    ok &= dev_alloc(&l.tokens, (size_t)DEC_MAX_BEAMS * DEC_TOK_LD, true);
+    ok &= dev_alloc(&l.fin_tokens, (size_t)DEC_MAX_BEAMS * DEC_TOK_LD, true);
+    ok &= dev_alloc(&l.cand_lp, (size_t)DEC_MAX_BEAMS * (DEC_MAX_BEAMS + 1));
+    ok &= dev_alloc(&l.cand_tok, (size_t)DEC_MAX_BEAMS * (DEC_MAX_BEAMS + 1));
+    ok &= dev_alloc(&l.ns_logits, (size_t)s.V);
+    ok &= dev_alloc(&l.part, 1, true);
+    ok &= cudaMallocHost((void**)&l.pin_done, 64) == cudaSuccess;
+    l.ready = ok;
+    return ok;
+}
+void decode_free_lanes() {                 // called when the decoder is closed (lane 0 must be active)
+    activate_lane(0);
+    for (int i = 1; i < MAX_LANES; ++i) {
+        Lane& l = g_parked[i];
+        if (l.stream) cudaStreamDestroy(l.stream);
+        dev_free(&l.mkv); dev_free(&l.table); dev_free(&l.slogits); dev_free(&l.mega_ll); dev_free(&l.mega_barrier); dev_free(&l.st);
+        dev_free(&l.tokens); dev_free(&l.fin_tokens); dev_free(&l.cand_lp); dev_free(&l.cand_tok); dev_free(&l.ns_logits); dev_free(&l.part);
+        if (l.pin_done) cudaFreeHost(l.pin_done);
+        l = Lane{};
+    }
+}
+
+struct DecodeJob { int n_initial, nb, k, sample_len, sot_index, steps; bool done; StepGraph* graph; };
+
+// state + prefill + first sampling step of the ACTIVE lane, all on `st` (the prefill workspaces are shared by the lanes)
+static void decode_begin(DecodeJob& j, const int* initial_tokens, int beam_size, int without_timestamps, int max_initial_timestamp_index) {
+    State& s = S();
+    DecodeCtx& c = g_dc;
     cudaStream_t st = s.stream;
-    const int d = s.d, k = beam_size > 0 ? nb + 1 : 1;
-    int sot_index = -1;
-    for (int i = 0; i < n_initial; ++i) if (initial_tokens[i] == c.spec.sot) sot_index = i;   // tokens.index(sot) (:617)
-    // ---- state ----
+    const int d = s.d, nb = j.nb, n_initial = j.n_initial;
     DecodeState h{};
-    h.L = n_initial; h.pos = n_initial - 1; h.sample_begin = n_initial; h.sample_len = sample_len;
+    h.L = n_initial; h.pos = n_initial - 1; h.sample_begin = n_initial; h.sample_len = j.sample_len;
     h.beam_mode = beam_size > 0; h.without_timestamps = without_timestamps; h.max_initial_ts = max_initial_timestamp_index;
     h.suppress_blank = 1; h.no_speech_prob = NAN;
     B200_CHECK(cudaMemcpyAsync(c.st, &h, sizeof(h), cudaMemcpyHostToDevice, st));
@@ -240,34 +301,44 @@ int b200DecodeWindow(const int* initial_tokens, int n_initial, int beam_size, in
         g.nb = nb; g.w_frag = s.tok_emb_frag; g.N = s.V; g.K = d; g.x_f32 = s.pout + (size_t)(n_initial - 1) * d; g.ld_x = 0;
         g.out_f32 = s.slogits; g.ld_out = s.V;
         step_gemv(g, st);                                               // logits of the last prompt row, same for every beam
-        if (sot_index >= 0) {
-            g.nb = 1; g.x_f32 = s.pout + (size_t)sot_index * d; g.out_f32 = c.ns_logits;
+        if (j.sot_index >= 0) {
+            g.nb = 1; g.x_f32 = s.pout + (size_t)j.sot_index * d; g.out_f32 = c.ns_logits;
             step_gemv(g, st);
             no_speech_prob(c.ns_logits, s.V, c.spec.no_speech, c.st, st);
         }
     }
     {
         StageTimer t(ST_SAMPLING);
-        launch_sampling(nb, k);
+        launch_sampling(nb, j.k);
     }
-    // ---- steps: i = 1 .. sample_len-1, polled every CHUNK steps for completion ----
-    int steps = 1;
-    bool done = false;
-    {
-        StageTimer t(ST_DECODER1);
-        if (steps < sample_len) { one_step(nb, k); ++steps; }           // eager once: sets kernel attributes before any capture
-        StepGraph* g = steps < sample_len ? step_graph(nb, k) : nullptr;
-        while (!done && steps < sample_len) {
-            // launches past sample_len / completion are no-ops: every kernel checks DecodeState::done first
-            if (g) { B200_CHECK(cudaGraphLaunch(g->exec, st)); g_launch_count += g->launches; }
-            else for (int i = 0; i < GRAPH_STEPS; ++i) one_step(nb, k);
-            steps += GRAPH_STEPS;
-            B200_CHECK(cudaMemcpyAsync(c.pin_done, &c.st->done, sizeof(int), cudaMemcpyDeviceToHost, st));
-            B200_CHECK(cudaStreamSynchronize(st));
-            done = *c.pin_done != 0;
-        }
+    j.steps = 1; j.done = false; j.graph = nullptr;
+}
+
+// issue the next GRAPH_STEPS steps of the ACTIVE lane and the read-back of its completion flag (no host sync)
+static void decode_issue(DecodeJob& j) {
+    State& s = S();
+    DecodeCtx& c = g_dc;
+    cudaStream_t st = s.stream;
+    if (j.steps == 1 && j.steps < j.sample_len) {                       // eager once: sets kernel attributes before any capture
+        one_step(j.nb, j.k); ++j.steps;
+        if (j.steps < j.sample_len) j.graph = step_graph(j.nb, j.k);
     }
-    // ---- finalize (decoding.py:411-431 / :320-325) ----
+    if (j.steps < j.sample_len) {
+        // launches past sample_len / completion are no-ops: every kernel checks DecodeState::done first
+        if (j.graph) { B200_CHECK(cudaGraphLaunch(j.graph->exec, st)); g_launch_count += j.graph->launches; }
+        else for (int i = 0; i < GRAPH_STEPS; ++i) one_step(j.nb, j.k);
+        j.steps += GRAPH_STEPS;
+    }
+    B200_CHECK(cudaMemcpyAsync(c.pin_done, &c.st->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+}
+
+// finalize (decoding.py:411-431 / :320-325) of the ACTIVE lane; its stream must be idle
+static int decode_finish(const DecodeJob& j, int* out_tokens, int* out_lengths, float* out_sum_logprobs, float* out_no_speech) {
+    State& s = S();
+    DecodeCtx& c = g_dc;
+    cudaStream_t st = s.stream;
+    const int nb = j.nb, n_initial = j.n_initial;
+    DecodeState h{};
     std::vector<int> tok((size_t)DEC_MAX_BEAMS * DEC_TOK_LD), fin((size_t)DEC_MAX_BEAMS * DEC_TOK_LD);
     B200_CHECK(cudaMemcpyAsync(&h, c.st, sizeof(h), cudaMemcpyDeviceToHost, st));
     B200_CHECK(cudaMemcpyAsync(tok.data(), c.tokens, tok.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -296,6 +367,97 @@ int b200DecodeWindow(const int* initial_tokens, int n_initial, int beam_size, in
     for (int i = n_cand; i < nb; ++i) { out_lengths[i] = -1; out_sum_logprobs[i] = -INFINITY; }
     if (out_no_speech) *out_no_speech = h.no_speech_prob;
     return h.step;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200DecodeWindows(const int* windows, int n_windows, const int* initial_tokens, int n_initial, int beam_size, int sample_len,
+                      int without_timestamps, int max_initial_timestamp_index, int* out_tokens, int* out_lengths,
+                      float* out_sum_logprobs, float* out_no_speech, int* out_steps) {
+    State& s = S();
+    DecodeCtx& c = g_dc;
+    if (!s.dec1_loaded || !s.dec256_loaded || !s.ckv_loaded) { record_error("b200DecodeWindows: decoder256 / decoder1 / crossKV not loaded"); return 0; }
+    const int nb = beam_size > 0 ? beam_size : 1;
+    if (nb > s.bs) { record_error("b200DecodeWindows: %d beams but loadDecoder256 reserved %d cache slots", nb, s.bs); return 0; }
+    if (n_initial < 1 || n_initial > PREFILL_CTX) { record_error("b200DecodeWindows: n_initial %d outside [1, 256]", n_initial); return 0; }
+    if (n_windows < 1 || sample_len < 1) return 0;
+    for (int w = 0; w < n_windows; ++w)
+        if (windows[w] < 0 || windows[w] >= (s.ckv_cap > 0 ? s.ckv_cap : 1)) { record_error("b200DecodeWindows: window %d outside [0, %d)", windows[w], s.ckv_cap); return 0; }
+    use_device();
+    activate_lane(0);
+    if (!ensure_decode_ctx()) return 0;
+    // lanes: only the persistent step kernel can share the GPU between decodes; B200_DECODE_LANES=1 turns the overlap off
+    static const int max_lanes = [] { const char* e = getenv("B200_DECODE_LANES"); const int v = e ? atoi(e) : MAX_LANES; return v < 1 ? 1 : (v > MAX_LANES ? MAX_LANES : v); }();
+    int lanes = mega_available() ? std::min(max_lanes, n_windows) : 1;
+    for (int i = 1; i < lanes; ++i) if (!ensure_lane(i)) { lanes = 1; break; }
+    const int cand = beam_size > 0 ? nb : 1;
+    int sot_index = -1;
+    for (int i = 0; i < n_initial; ++i) if (initial_tokens[i] == c.spec.sot) sot_index = i;   // tokens.index(sot) (:617)
+    cudaStream_t main_stream = s.stream;
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr};
+    if (lanes > 1) { cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming); for (int i = 1; i < lanes; ++i) cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming); }
+    int total_steps = 0;
+    for (int w0 = 0; w0 < n_windows; w0 += lanes) {
+        const int n = std::min(lanes, n_windows - w0);
+        DecodeJob job[MAX_LANES];
+        // ---- prefill of every lane on the main stream (shared workspaces), then fork ----
+        for (int i = 0; i < n; ++i) {
+            activate_lane(i);
+            cudaStream_t own = S().stream;
+            S().stream = main_stream;
+            S().cur_window = windows[w0 + i];
+            job[i] = DecodeJob{n_initial, nb, beam_size > 0 ? nb + 1 : 1, sample_len, sot_index, 0, false, nullptr};
+            decode_begin(job[i], initial_tokens, beam_size, without_timestamps, max_initial_timestamp_index);
+            S().stream = own;
+        }
+        activate_lane(0);
+        s.mega_ctas = n > 1 ? s.n_sms / n : 0;
+        {
+            StageTimer t(ST_DECODER1);                                  // on the main stream: fork .. join of all lanes
+            if (n > 1) { B200_CHECK(cudaEventRecord(ev_fork, main_stream)); }
+            for (int i = 1; i < n; ++i) { activate_lane(i); B200_CHECK(cudaStreamWaitEvent(S().stream, ev_fork, 0)); }
+            // ---- steps: every lane advances GRAPH_STEPS per round; completion is polled once per round ----
+            bool any = true;
+            while (any) {
+                for (int i = 0; i < n; ++i) if (!job[i].done && job[i].steps < sample_len) { activate_lane(i); decode_issue(job[i]); }
+                any = false;
+                for (int i = 0; i < n; ++i) {
+                    if (job[i].done) continue;
+                    activate_lane(i);
+                    B200_CHECK(cudaStreamSynchronize(S().stream));
+                    if (*g_dc.pin_done != 0 || job[i].steps >= sample_len) job[i].done = true; else any = true;
+                }
+            }
+            for (int i = 1; i < n; ++i) { activate_lane(i); B200_CHECK(cudaEventRecord(ev_join[i], S().stream)); B200_CHECK(cudaStreamWaitEvent(main_stream, ev_join[i], 0)); }
+            activate_lane(0);
+        }
+        s.mega_ctas = 0;
+        for (int i = 0; i < n; ++i) {
+            activate_lane(i);
+            const size_t o = (size_t)(w0 + i);
+            const int steps = decode_finish(job[i], out_tokens + o * cand * DEC_TOK_LD, out_lengths + o * cand, out_sum_logprobs + o * cand,
+                                            out_no_speech ? out_no_speech + o : nullptr);
+            if (out_steps) out_steps[o] = steps;
+            total_steps += steps;
+        }
+        activate_lane(0);
+    }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    for (int i = 1; i < MAX_LANES; ++i) if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+    return total_steps;
+}
+
+int b200DecodeWindow(const int* initial_tokens, int n_initial, int beam_size, int sample_len, int without_timestamps,
+                     int max_initial_timestamp_index, int* out_tokens, int* out_lengths, float* out_sum_logprobs,
+                     float* out_no_speech) {
+    activate_lane(0);
+    const int w = S().cur_window;
+    return b200DecodeWindows(&w, 1, initial_tokens, n_initial, beam_size, sample_len, without_timestamps, max_initial_timestamp_index,
+                             out_tokens, out_lengths, out_sum_logprobs, out_no_speech, nullptr);
 }
 
 void decoder1StepFused(const int* tokens_hist, int n_hist, int sample_begin, int text_offset, int without_timestamps,

@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decoder_mega_kernel(const __gri
         const uint32_t ep = seq * 64u + (uint32_t)l + 1u, ep_prev = ep - 1u;      // ep_prev: x3 of the layer below
         if (st == ST_SA) {
             dbg.mark(2 * it + 1);
-            stage_self_attn(sm, a, L.cache_k, L.cache_v, ep, pos, cta, nctas, stage_rot(ST_SA, nctas), warp, lane);
+            stage_self_attn(sm, a, a.mkv + (long)(2 * l) * a.kv_stride, a.mkv + (long)(2 * l + 1) * a.kv_stride, ep, pos, cta, nctas, stage_rot(ST_SA, nctas), warp, lane);
             dbg.mark(2 * it + 2);
             continue;
         }

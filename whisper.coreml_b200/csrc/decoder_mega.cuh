@@ -13,7 +13,6 @@ struct MegaLayer {
     const bf16 *qkv, *attn_out, *cross_q, *cross_out, *mlp1, *mlp2;                  // fragment-major weights
     const float *qkv_b, *attn_out_b, *cross_q_b, *cross_out_b, *mlp1_b, *mlp2_b;
     const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *ln3_w, *ln3_b;
-    bf16 *cache_k, *cache_v;                                                          // [slots][448][d]
 };
 struct MegaModel {                      // lives in device memory, built when both decoders are loaded
     int d, H, Ld, V, n_tiles_vocab;
@@ -34,6 +33,7 @@ struct MegaArgs {
     uint2 *ll_cap;                      // [H][7][8][66] fp32 cross-attention partials (max, sum, o[64]) per key split
     uint2 *ll_hid;                      // [8][2d]   bf16x2 MLP hidden activations
     float* logits; long ld_logits;
+    bf16* mkv; long kv_stride;          // KV cache [2Ld][slots][448][d] of this decode lane; elements per [slots][448][d] plane
     int* table; int* tokens;            // KV slot table [8][448]; token histories [8][DEC_TOK_LD] (nullptr with x_in)
     // device-resident decode loop (do_sampling): logit filters + top-k + beam update run in the kernel's tail
     int do_sampling, k; DecodeState* st; DecodeSpec spec; SamplePartials* sp; float* cand_lp; int* cand_tok; int* fin_tokens;

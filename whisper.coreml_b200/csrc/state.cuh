@@ -22,6 +22,8 @@ struct DecLayer {
     DecLinear qkv, attn_out, cross_q, cross_out, mlp1, mlp2;
 };
 
+constexpr int MAX_LANES = 2;              // window decodes that may run concurrently, each on its share of the SMs
+
 struct State {
     int device = 0;
     cudaStream_t stream = nullptr;    // library stream (non-blocking, capturable); created by use_device()
@@ -75,6 +77,7 @@ struct State {
     unsigned* mega_barrier = nullptr; // [0] arrivals, [1] leavers, [2] launch sequence number
     int smem_optin = 0;
     unsigned long long* mega_dbg = nullptr;   // stage timeline buffer (b200TestStepTimeline)
+    int mega_ctas = 0;                // CTAs of the next persistent step launch (0 = all SMs)
     int step_impl = -1;               // -1 undecided, 0 persistent kernel, 1 one kernel per stage (B200_STEP_IMPL=v1)
     int n_sms = 0;
     float* pin_logits = nullptr;      // pinned host staging
@@ -121,6 +124,7 @@ void run_cross_kv(int n_windows);
 void run_prefill(int beam_idx, bool want_chw);                            // px/pmask -> pout (+ pchw), KV rows -> slot
 // sx -> slogits; d_t / d_skip: optional device-side text_offset and no-op flag (device-driven decode loop)
 void run_step(int nb, int text_offset, const float* d_mask, bool want_logits, const int* d_t, const int* d_skip);
-bool mega_available();               // persistent step kernel usable for the loaded model?
+bool mega_available();
+void decode_free_lanes();            // api_decode.cu: releases the extra decode lanes               // persistent step kernel usable for the loaded model?
 
 }  // namespace b200

@@ -37,16 +37,18 @@ class DecodingResult:                        # whisper/decoding.py:118-128
     candidates: int = 0
 
 
-def decode(model, options: DecodingOptions = DecodingOptions(), window: Optional[int] = None) -> DecodingResult:
-    """DecodingTask.run (decoding.py:740-816) for the window already encoded on the device."""
+def decode_windows(model, options: DecodingOptions, windows: Sequence[int]) -> List[DecodingResult]:
+    """DecodingTask.run (decoding.py:740-816) for several windows already encoded on the device.  The windows are
+    independent (condition_on_previous_text=False), so the library decodes them concurrently (b200DecodeWindows)."""
     if options.temperature != 0.0:
         raise NotImplementedError("sampling at temperature > 0 (decoding.py:307-310) is not on the B200 hot path")
     if options.patience not in (None, 1.0):
         raise NotImplementedError("patience != 1")
     if options.prompt:
         raise NotImplementedError("prompt conditioning: windows are decoded independently (condition_on_previous_text=False)")
-    if window is not None:
-        model.select_window(window)
+    windows = [int(w) for w in windows]
+    if not windows:
+        return []
     sp = model.specials
     initial = list(sp.sot_sequence) + ([sp.no_timestamps] if options.without_timestamps else [])
     n_ctx = model.dims.n_text_ctx
@@ -56,24 +58,37 @@ def decode(model, options: DecodingOptions = DecodingOptions(), window: Optional
     max_ts = -1
     if options.max_initial_timestamp:
         max_ts = round(options.max_initial_timestamp / 0.02)              # decoding.py:591-594 (time_precision 30/1500)
+    nw = len(windows)
     init = np.array(initial, dtype=np.int32)
-    toks = np.empty((n_cand, n_ctx + 1), dtype=np.int32)
-    lens = np.empty(n_cand, dtype=np.int32); lps = np.empty(n_cand, dtype=np.float32); nsp = np.empty(1, dtype=np.float32)
-    steps = model.lib.b200DecodeWindow(init.ctypes.data_as(_lib.i32p), len(init), bs, sample_len,
-                                       1 if options.without_timestamps else 0, max_ts,
-                                       toks.ctypes.data_as(_lib.i32p), lens.ctypes.data_as(_lib.i32p),
-                                       lps.ctypes.data_as(_lib.f32p), nsp.ctypes.data_as(_lib.f32p))
-    _lib.check_errors("b200DecodeWindow")
-    valid = [i for i in range(n_cand) if lens[i] >= 0]
-    if not valid:
-        raise RuntimeError("b200DecodeWindow returned no candidate")
-    if options.length_penalty is None:                                   # decoding.py:226-233
-        with np.errstate(divide="ignore", invalid="ignore"):
-            scores = [float(lps[i]) / float(lens[i]) for i in valid]
-    else:
-        scores = [float(lps[i]) / (((5 + int(lens[i])) / 6) ** options.length_penalty) for i in valid]
-    best = valid[int(np.argmax(scores))]
+    wins = np.array(windows, dtype=np.int32)
+    toks = np.empty((nw, n_cand, n_ctx + 1), dtype=np.int32)
+    lens = np.empty((nw, n_cand), dtype=np.int32); lps = np.empty((nw, n_cand), dtype=np.float32)
+    nsp = np.empty(nw, dtype=np.float32); steps = np.zeros(nw, dtype=np.int32)
+    model.lib.b200DecodeWindows(wins.ctypes.data_as(_lib.i32p), nw, init.ctypes.data_as(_lib.i32p), len(init), bs, sample_len,
+                                1 if options.without_timestamps else 0, max_ts,
+                                toks.ctypes.data_as(_lib.i32p), lens.ctypes.data_as(_lib.i32p),
+                                lps.ctypes.data_as(_lib.f32p), nsp.ctypes.data_as(_lib.f32p), steps.ctypes.data_as(_lib.i32p))
+    _lib.check_errors("b200DecodeWindows")
+    out = []
     n0 = len(initial)
-    tokens = toks[best, n0:n0 + lens[best]].tolist()
-    return DecodingResult(tokens=tokens, avg_logprob=float(lps[best]) / (len(tokens) + 1), no_speech_prob=float(nsp[0]),
-                          sum_logprob=float(lps[best]), steps=int(steps), candidates=len(valid))
+    for w in range(nw):
+        valid = [i for i in range(n_cand) if lens[w, i] >= 0]
+        if not valid:
+            raise RuntimeError("b200DecodeWindows returned no candidate")
+        if options.length_penalty is None:                               # decoding.py:226-233
+            with np.errstate(divide="ignore", invalid="ignore"):
+                scores = [float(lps[w, i]) / float(lens[w, i]) for i in valid]
+        else:
+            scores = [float(lps[w, i]) / (((5 + int(lens[w, i])) / 6) ** options.length_penalty) for i in valid]
+        best = valid[int(np.argmax(scores))]
+        tokens = toks[w, best, n0:n0 + lens[w, best]].tolist()
+        out.append(DecodingResult(tokens=tokens, avg_logprob=float(lps[w, best]) / (len(tokens) + 1), no_speech_prob=float(nsp[w]),
+                                  sum_logprob=float(lps[w, best]), steps=int(steps[w]), candidates=len(valid)))
+    return out
+
+
+def decode(model, options: DecodingOptions = DecodingOptions(), window: Optional[int] = None) -> DecodingResult:
+    """DecodingTask.run (decoding.py:740-816) for one window already encoded on the device."""
+    if window is not None:
+        model.select_window(window)
+    return decode_windows(model, options, [model.current_window])[0]

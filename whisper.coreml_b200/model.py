@@ -149,6 +149,8 @@ class WhisperB200:
         return logits, cross_qks, dummy
 
     # ---- device-resident fast path --------------------------------------------------------------------------
+    current_window = 0
+
     def encode_windows(self, mel: torch.Tensor, seeks: Sequence[int]) -> int:
         """Batched encoder + crossKV over independent windows of a device-resident log-mel (n_mels, frames)."""
         self.load()
@@ -160,11 +162,13 @@ class WhisperB200:
         self.lib.crossKVPredictWindows(len(arr))
         _lib.check_errors("encode_windows")
         self.n_windows = len(arr)
+        self.current_window = 0
         return self.n_windows
 
     def select_window(self, w: int):
         self.lib.b200SelectWindow(w)
         _lib.check_errors("select_window")
+        self.current_window = int(w)
 
     def stage_times_ms(self, reset: bool = False) -> Dict[str, float]:
         buf = (ctypes.c_float * 7)()

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .audio import FRAMES_PER_SECOND, HOP_LENGTH, N_FRAMES, N_SAMPLES, SAMPLE_RATE, log_mel_spectrogram
-from .decoding import DecodingOptions, DecodingResult, decode
+from .decoding import DecodingOptions, DecodingResult, decode, decode_windows
 from .timing import align_tokens
 
 
@@ -68,8 +68,10 @@ def transcribe(model, audio: torch.Tensor, *, beam_size: Optional[int] = 5, word
     for b0 in range(0, len(mine), window_batch):
         batch = mine[b0:b0 + window_batch]
         model.encode_windows(mel, batch)
+        results = decode_windows(model, opts, range(len(batch)))          # independent windows decode concurrently on the device
         for w, seek in enumerate(batch):
-            result = decode(model, opts, window=w)
+            result = results[w]
+            model.select_window(w)                                        # word timestamps below read this window's cross K/V
             decode_steps.append(result.steps)
             segment_size = min(N_FRAMES, content_frames - seek)
             time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
