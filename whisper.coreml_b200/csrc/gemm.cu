@@ -3,7 +3,9 @@
 //   warp 0 (1 thread)  : TMA producer   - cp.async.bulk.tensor into a STAGES-deep smem ring
 //   warp 1 (1 thread)  : MMA issuer     - tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16,
 //                                          accumulators in TMEM, double buffered (2 x BLOCK_N columns)
-//   warps 2..5         : epilogue       - tcgen05.ld -> bias / GELU / residual -> global
+//   warps 2..9         : epilogue       - tcgen05.ld -> bias / GELU / residual -> global; two warps per TMEM
+//                                          lane quadrant take alternate 32-column chunks (the epilogue, not the MMA,
+//                                          bounded the tile time with four warps)
 //
 // The epilogue of tile i overlaps the main loop of tile i+1 through the tmem_full / tmem_empty
 // mbarrier pair.  Operands are bf16, K-major, 128-byte swizzled (TMA SWIZZLE_128B <-> UMMA
@@ -18,7 +20,7 @@ namespace b200 {
 
 static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int GEMM_THREADS = 320;             // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
 
 struct GemmKernelArgs {
     int num_a_maps, kblocks_per_map, num_kb;
@@ -65,7 +67,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         tma_prefetch_desc(&mapA0);
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -116,6 +118,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     } else if (warp >= 2) {
         // ------------------------------ epilogue ------------------------------
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;                   // the two warps of a quadrant take alternate 32-column chunks
         int a = 0; uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int n_blk = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
@@ -128,28 +131,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             mbar_wait(&tmem_full[a], aph);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
+            for (int c = half; c < BLOCK_N / 32; c += 2) {
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + a * BLOCK_N + c * 32, r);
                 tmem_ld_wait();
                 const int n0 = n_blk * BLOCK_N + c * 32;
-                if (!row_ok || n0 >= g.N) continue;
+                if (n0 >= g.N) continue;                    // warp uniform
                 float v[32];
                 const bool full = g.vec_ok && n0 + 32 <= g.N;
+                // one coalesced bias load per chunk (lane i holds column n0 + i), broadcast by shuffle: written as 32 scalar
+                // loads ptxas serialised them through two registers and the epilogue, not the MMA, set the tile time
+                const float bv = (g.bias && n0 + lane < g.N) ? __ldg(g.bias + n0 + lane) : 0.f;
+                float4 q[8];
+                if (add_row && full && row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) q[i] = *reinterpret_cast<const float4*>(add_row + n0 + 4 * i);
+                }
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     float x = __uint_as_float(r[i]);
-                    if (g.bias && n0 + i < g.N) x += __ldg(g.bias + n0 + i);
+                    if (g.bias) x += __shfl_sync(0xffffffffu, bv, i);
                     if (g.gelu) x = gelu_erf(x);
                     v[i] = x;
                 }
+                if (!row_ok) continue;                      // rows past the batch: nothing to add or store (after the shuffles)
                 if (add_row) {
                     if (full) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            float4 q = *reinterpret_cast<const float4*>(add_row + n0 + i);
-                            v[i] += q.x; v[i + 1] += q.y; v[i + 2] += q.z; v[i + 3] += q.w;
-                        }
+                        for (int i = 0; i < 8; ++i) { v[4 * i] += q[i].x; v[4 * i + 1] += q[i].y; v[4 * i + 2] += q[i].z; v[4 * i + 3] += q[i].w; }
                     } else {
                         for (int i = 0; i < 32 && n0 + i < g.N; ++i) v[i] += add_row[n0 + i];
                     }
