@@ -151,9 +151,12 @@ __global__ void fill_table_kernel(int* table, int beam, int n, int value) {
     if (i < n) table[beam * N_TEXT_CTX + i] = value;
 }
 
-void run_prefill(int beam_idx, bool want_chw) {
+// rows < 256: only the first `rows` positions are computed.  The reference computes and stores all 256 rows, pad rows
+// included (decoder.py:214, coreml.mm:313-326), but rows >= n_ctx of x / CHW are sliced away (decoder.py:236-237) and their
+// K/V rows are masked by text_offset until the step that overwrites them, so the device-resident decode loop skips them.
+void run_prefill(int beam_idx, bool want_chw, int rows) {
     State& s = S();
-    const int d = s.d, M = PREFILL_CTX;
+    const int d = s.d, M = rows < 1 ? 1 : (rows > PREFILL_CTX ? PREFILL_CTX : rows);
     cudaStream_t st = s.stream;
     for (int l = 0; l < s.Ld; ++l) {
         const DecLayer& L = s.dec_layers[l];
@@ -166,7 +169,7 @@ void run_prefill(int beam_idx, bool want_chw) {
         a.Q = s.pqkv; a.K = s.pqkv + d; a.V = s.pqkv + 2 * d; a.ldq = a.ldk = a.ldv = 3L * d;
         a.q_head_stride = a.k_head_stride = a.v_head_stride = 64;
         a.O = s.patt; a.ldo = d; a.o_head_stride = 64;
-        a.n_q = a.n_k = M; a.n_head = s.H; a.batch = 1; a.mask = s.pmask; a.ld_mask = M;
+        a.n_q = a.n_k = M; a.n_head = s.H; a.batch = 1; a.mask = s.pmask; a.ld_mask = PREFILL_CTX;
         attention_simt(a, st);
         GemmParams po = lin(s.patt, M, d, L.attn_out.w, L.attn_out.b, d, s.px, true);
         po.add = s.px; po.add_rows = M; po.ld_add = d;
@@ -181,7 +184,7 @@ void run_prefill(int beam_idx, bool want_chw) {
         c.n_q = M; c.n_k = N_AUDIO_CTX; c.n_head = s.H; c.batch = 1;
         if (want_chw && s.n_align > 0) {                                // raw QK of the alignment heads (decoder.py:306-308)
             c.qk_dump = s.pchw; c.dump_slot = s.d_dump_slot + l * s.H; c.dump_ld = N_AUDIO_CTX;
-            c.dump_slot_stride = (long)M * N_AUDIO_CTX;
+            c.dump_slot_stride = (long)PREFILL_CTX * N_AUDIO_CTX;
         }
         attention_simt(c, st);
         GemmParams pc = lin(s.patt, M, d, L.cross_out.w, L.cross_out.b, d, s.px, true);
@@ -315,7 +318,8 @@ bool run_step_mega(int nb, int text_offset, const float* d_mask, const float* d_
     a.ll_cap = p; p += (size_t)s.H * 7 * 8 * 66; a.ll_hid = p;
     a.logits = s.slogits; a.ld_logits = s.V; a.table = s.table; a.mkv = s.mkv; a.kv_stride = (long)s.bs * N_TEXT_CTX * s.d;
     a.mask = d_mask; a.x_in = d_x_in; a.text_offset = text_offset; a.barrier = s.mega_barrier; a.seq = s.mega_barrier + 2; a.dbg = s.mega_dbg;
-    return mega_launch(a, s.mega_ctas > 0 ? s.mega_ctas : s.n_sms, s.stream);
+    static const int force_ctas = getenv("B200_MEGA_CTAS") ? atoi(getenv("B200_MEGA_CTAS")) : 0;      // experiments: fixed grid size
+    return mega_launch(a, force_ctas > 0 ? force_ctas : (s.mega_ctas > 0 ? s.mega_ctas : s.n_sms), s.stream);
 }
 size_t mega_ll_words_for(size_t d, size_t H);
 static size_t mega_ll_words(size_t d, size_t H) { return mega_ll_words_for(d, H); }
@@ -517,7 +521,7 @@ void decoder256Predict(float* x, float* qk_mask, float* out_x, float* out_cross_
     const size_t d = s.d, M = PREFILL_CTX;
     B200_CHECK(cudaMemcpyAsync(s.px, x, M * d * sizeof(float), cudaMemcpyHostToDevice, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.pmask, qk_mask, M * M * sizeof(float), cudaMemcpyHostToDevice, s.stream));
-    run_prefill(beam_idx, out_cross_head_weights != nullptr);
+    run_prefill(beam_idx, out_cross_head_weights != nullptr, PREFILL_CTX);
     B200_CHECK(cudaMemcpyAsync(out_x, s.pout, M * d * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     if (out_cross_head_weights && s.n_align > 0)
         B200_CHECK(cudaMemcpyAsync(out_cross_head_weights, s.pchw, (size_t)s.n_align * M * N_AUDIO_CTX * sizeof(float),

@@ -100,7 +100,7 @@ void decode_clear_graphs() {
 
 bool run_step_mega(int nb, int text_offset, const float* d_mask, const float* d_x_in, const MegaArgs* decode_fields);
 
-static void launch_sampling(int nb, int k);
+static void launch_sampling(int nb, int k, bool shared_logits = false);
 static void one_step(int nb, int k) {
     State& s = S();
     DecodeCtx& c = g_dc;
@@ -138,11 +138,12 @@ static StepGraph* step_graph(int nb, int k) {
     return &g_step_graphs.emplace(key, g).first->second;
 }
 
-static void launch_sampling(int nb, int k) {
+// shared_logits: every beam reads logits row 0 (the first step after the prompt: all beams hold the same tokens)
+static void launch_sampling(int nb, int k, bool shared_logits) {
     State& s = S();
     DecodeCtx& c = g_dc;
     SampleArgs sa{};
-    sa.logits = s.slogits; sa.ld_logits = s.V; sa.tokens = c.tokens; sa.st = c.st; sa.spec = c.spec; sa.nb = nb; sa.k = k;
+    sa.logits = s.slogits; sa.ld_logits = shared_logits ? 0 : s.V; sa.tokens = c.tokens; sa.st = c.st; sa.spec = c.spec; sa.nb = nb; sa.k = k;
     sa.cand_lp = c.cand_lp; sa.cand_tok = c.cand_tok; sa.part = c.part;
     sample_partial(sa, s.stream);
     BeamUpdateArgs ba{};
@@ -290,11 +291,27 @@ static void decode_begin(DecodeJob& j, const int* initial_tokens, int beam_size,
     B200_CHECK(cudaMemcpyAsync(d_init, initial_tokens, (size_t)n_initial * sizeof(int), cudaMemcpyHostToDevice, st));
     init_tokens_kernel<<<1, 256, 0, st>>>(c.tokens, d_init, n_initial, nb, c.spec.eot, s.table);
     B200_LAUNCH_CHECK();
-    {   // ---- prefill once: all beams hold the same initial tokens (decoding.py:761) ----
+    const bool by_steps = mega_available();
+    if (by_steps) {
+        // ---- prompt, all beams hold the same tokens (decoding.py:761): n_initial single-beam token steps of the persistent
+        //      kernel into cache slot 0 (every beam's slot table points there).  A causal prefill over n rows IS n steps; the
+        //      step kernel streams each weight once per position instead of launching ~50 mostly idle kernels per window.
+        StageTimer t(ST_DECODER256);
+        const int saved_ctas = s.mega_ctas;
+        s.mega_ctas = 0;                                                // the prompt runs alone on the main stream: all SMs
+        for (int p = 0; p < n_initial; ++p) {
+            MegaArgs a{};
+            a.tokens = c.tokens;
+            a.no_vocab = !(p == n_initial - 1 || p == j.sot_index);
+            run_step_mega(1, p, nullptr, nullptr, &a);
+            if (p == j.sot_index) no_speech_prob(s.slogits, s.V, c.spec.no_speech, c.st, st);   // logits of the sot position (:716-720)
+        }
+        s.mega_ctas = saved_ctas;
+    } else {   // ---- prefill once: all beams hold the same initial tokens (decoding.py:761) ----
         StageTimer t(ST_DECODER256);
         prefill_inputs_kernel<<<PREFILL_CTX, 256, 0, st>>>(s.tok_emb, s.pos_emb, d_init, n_initial, d, s.px, s.pmask);
         B200_LAUNCH_CHECK();
-        run_prefill(0, false);
+        run_prefill(0, false, n_initial);
         init_tokens_kernel<<<1, 256, 0, st>>>(c.tokens, d_init, n_initial, nb, c.spec.eot, s.table);   // run_prefill marked slot 0 only
         B200_LAUNCH_CHECK();
         StepGemv g{};
@@ -309,7 +326,7 @@ static void decode_begin(DecodeJob& j, const int* initial_tokens, int beam_size,
     }
     {
         StageTimer t(ST_SAMPLING);
-        launch_sampling(nb, j.k);
+        launch_sampling(nb, j.k, by_steps);
     }
     j.steps = 1; j.done = false; j.graph = nullptr;
 }
@@ -519,7 +536,7 @@ int b200AlignTokens(const int* tokens, int n_tokens, int n_skip, int num_frames,
     B200_CHECK(cudaMemcpyAsync(a.d_tok, tokens, (size_t)n_tokens * sizeof(int), cudaMemcpyHostToDevice, st));
     prefill_inputs_kernel<<<PREFILL_CTX, 256, 0, st>>>(s.tok_emb, s.pos_emb, a.d_tok, n_tokens, s.d, s.px, s.pmask);
     B200_LAUNCH_CHECK();
-    run_prefill(0, true);                                               // model(tokens[None]) (timing.py:185, model.py:110-119)
+    run_prefill(0, true, n_tokens);                                     // model(tokens[None]) (timing.py:185, model.py:110-119)
     alignment_matrix_dev(s.pchw, s.n_align, PREFILL_CTX, n_tokens, F, n_skip, medfilt_width, a.tmp, a.mat, false, st);
     negate_kernel<<<cdiv(n_rows * F, 256), 256, 0, st>>>(a.mat, a.neg, (long)n_rows * F);   // dtw(-matrix) (timing.py:205)
     B200_LAUNCH_CHECK();

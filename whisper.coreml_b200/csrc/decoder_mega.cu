@@ -63,6 +63,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // A protocol bug traps (-> launch error) instead of hanging the GPU box.
@@ -727,7 +730,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decoder_mega_kernel(const __gri
     __syncthreads();
 
     const int pos = a.d_pos ? *a.d_pos : a.text_offset;    // text_offset of this step
-    const int n_stages = M.Ld * 8 + 1;
+    const int n_stages = M.Ld * 8 + (a.no_vocab ? 0 : 1);
 
     if (warp == MG_CWARPS) {
         // =========================================== producer ===========================================
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decoder_mega_kernel(const __gri
         constexpr int n_ktiles = CROSS_KEYS_PAD / 16, n_vkc = CROSS_KEYS_PAD / 32;
         const long head_elems = (long)64 * CROSS_KEYS_PAD;
         for (int it = 0; it < n_stages; ++it) {
-            const int l = it >> 3, st = it == n_stages - 1 ? ST_VOCAB : (it & 7);
+            const int l = it >> 3, st = it == M.Ld * 8 ? ST_VOCAB : (it & 7);
             if (st == ST_SA) continue;
             if (st == ST_CA) {
                 for (int u = (cta + stage_rot(ST_CA, nctas)) % nctas; u < H * MG_N_SPLITS; u += nctas) {
@@ -792,7 +795,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decoder_mega_kernel(const __gri
     dbg.mark(0);
 
     for (int it = 0; it < n_stages; ++it) {
-        const int l = it >> 3, st = it == n_stages - 1 ? ST_VOCAB : (it & 7);
+        const int l = it >> 3, st = it == M.Ld * 8 ? ST_VOCAB : (it & 7);
         const MegaLayer& L = M.layers[l < M.Ld ? l : 0];
         const uint32_t ep = seq * 64u + (uint32_t)l + 1u, ep_prev = ep - 1u;      // ep_prev: x3 of the layer below
         if (st == ST_SA) {
@@ -838,19 +841,59 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decoder_mega_kernel(const __gri
         unsigned bar_k = 0;
         grid_sync(a.barrier, bar_k, nctas, tid);
         dbg.mark(2 * n_stages + 1);
-        SampleArgs sa;                             // logit filters + partial log-softmax / top-k per (chunk, beam)
-        sa.logits = a.logits; sa.ld_logits = a.ld_logits; sa.tokens = a.tokens; sa.st = a.st; sa.spec = a.spec; sa.nb = a.nb; sa.k = a.k;
-        sa.part = a.sp; sa.cand_lp = a.cand_lp; sa.cand_tok = a.cand_tok;
-        for (int u = cta; u < SAMPLE_CHUNKS * a.nb; u += nctas) sample_partial_body<MG_CONSUMERS>(sa, u % SAMPLE_CHUNKS, u / SAMPLE_CHUNKS, tid, ConsumerSync());
+        // Everything the two phases read is first copied into shared memory with 4-byte cp.async (one L2 round trip, all
+        // in flight together); the generic bodies of sampling_dev.cuh then run against those copies.
+        uint8_t* scratch = reinterpret_cast<uint8_t*>(sm.xs);
+        const int tb = a.spec.timestamp_begin, V = a.spec.n_vocab;
+        for (int u = cta; u < SAMPLE_CHUNKS * a.nb; u += nctas) {
+            const int chunk = u % SAMPLE_CHUNKS, b = u / SAMPLE_CHUNKS;
+            int lo, hi;
+            if (chunk < SAMPLE_TEXT_CHUNKS) { const int per = (tb + SAMPLE_TEXT_CHUNKS - 1) / SAMPLE_TEXT_CHUNKS; lo = chunk * per; hi = min(tb, lo + per); }
+            else { lo = tb; hi = V; }
+            float* s_logits = reinterpret_cast<float*>(scratch);                       // [<= 2048]
+            uint8_t* s_sup = scratch + 8192;                                            // [<= 2064] suppress flags from lo & ~3
+            int* s_tok = reinterpret_cast<int*>(scratch + 8192 + 2176);                 // [449] token row of beam b
+            DecodeState* s_st = reinterpret_cast<DecodeState*>(scratch + 8192 + 2176 + 1856);
+            consumer_sync();
+            const float* gl = a.logits + (long)b * a.ld_logits + lo;
+            for (int i = tid; i < hi - lo; i += MG_CONSUMERS) cp_async4(s_logits + i, gl + i);
+            const int lo4 = lo & ~3;
+            for (int i = tid; i < (hi - lo4 + 3) / 4; i += MG_CONSUMERS) cp_async4(s_sup + 4 * i, a.spec.d_suppress + lo4 + 4 * i);
+            for (int i = tid; i < DEC_TOK_LD; i += MG_CONSUMERS) cp_async4(s_tok + i, a.tokens + b * DEC_TOK_LD + i);
+            for (int i = tid; i < (int)(sizeof(DecodeState) / 4); i += MG_CONSUMERS) cp_async4(reinterpret_cast<int*>(s_st) + i, reinterpret_cast<const int*>(a.st) + i);
+            cp_async_wait_all();
+            consumer_sync();
+            SampleArgs sa;                         // the bodies index by absolute token / beam: rebase the pointers onto the copies
+            sa.logits = s_logits - ((long)b * a.ld_logits + lo); sa.ld_logits = a.ld_logits; sa.tokens = s_tok - b * DEC_TOK_LD; sa.st = s_st;
+            sa.spec = a.spec; sa.spec.d_suppress = s_sup - lo4; sa.nb = a.nb; sa.k = a.k;
+            sa.part = a.sp; sa.cand_lp = a.cand_lp; sa.cand_tok = a.cand_tok;
+            sample_partial_body<MG_CONSUMERS>(sa, chunk, b, tid, ConsumerSync());
+        }
         dbg.mark(2 * n_stages + 2);
         grid_sync(a.barrier, bar_k, nctas, tid);
         dbg.mark(2 * n_stages + 3);
         if (cta == 0) {                            // merge + greedy / beam update
+            SamplePartials* s_part = reinterpret_cast<SamplePartials*>(scratch);
+            constexpr int PART_BYTES = (int)((sizeof(SamplePartials) + 127) / 128 * 128);
+            int* stage = reinterpret_cast<int*>(scratch + PART_BYTES);                 // [8][449] token rows
+            int* stage2 = stage + DEC_MAX_BEAMS * DEC_TOK_LD;                            // [8][448] slot table
+            DecodeState* s_st = reinterpret_cast<DecodeState*>(stage2 + DEC_MAX_BEAMS * 448);
+            consumer_sync();
+            for (int i = tid; i < (int)(sizeof(SamplePartials) / 4); i += MG_CONSUMERS) cp_async4(reinterpret_cast<int*>(s_part) + i, reinterpret_cast<const int*>(a.sp) + i);
+            for (int i = tid; i < a.nb * DEC_TOK_LD; i += MG_CONSUMERS) cp_async4(stage + i, a.tokens + i);
+            for (int i = tid; i < a.nb * 448; i += MG_CONSUMERS) cp_async4(stage2 + i, a.table + i);
+            for (int i = tid; i < (int)(sizeof(DecodeState) / 4); i += MG_CONSUMERS) cp_async4(reinterpret_cast<int*>(s_st) + i, reinterpret_cast<const int*>(a.st) + i);
+            cp_async_wait_all();
+            consumer_sync();
             BeamUpdateArgs ba;
-            ba.part = a.sp; ba.timestamp_begin = a.spec.timestamp_begin; ba.update = 1; ba.cand_lp = a.cand_lp; ba.cand_tok = a.cand_tok;
-            ba.nb = a.nb; ba.k = a.k; ba.tokens = a.tokens; ba.table = a.table; ba.fin_tokens = a.fin_tokens; ba.st = a.st;
+            ba.part = s_part; ba.timestamp_begin = a.spec.timestamp_begin; ba.update = 1; ba.cand_lp = a.cand_lp; ba.cand_tok = a.cand_tok;
+            ba.nb = a.nb; ba.k = a.k; ba.tokens = a.tokens; ba.table = a.table; ba.fin_tokens = a.fin_tokens; ba.st = s_st;
             ba.eot = a.spec.eot; ba.n_text_ctx = N_TEXT_CTX;
-            beam_update_body<MG_CONSUMERS>(ba, reinterpret_cast<int*>(sm.xs), tid, ConsumerSync());
+            const int was_done = s_st->done;
+            beam_update_body<MG_CONSUMERS, true>(ba, stage, stage2, tid, ConsumerSync());
+            consumer_sync();
+            if (!was_done)                         // publish the updated decode state (pos / done steer the next launch)
+                for (int i = tid; i < (int)(sizeof(DecodeState) / 4); i += MG_CONSUMERS) reinterpret_cast<int*>(a.st)[i] = reinterpret_cast<const int*>(s_st)[i];
         }
         dbg.mark(2 * n_stages + 4);
     }

@@ -41,6 +41,7 @@ struct MegaArgs {
     const float* mask;                  // reference ABI: additive (449) mask on the device, else nullptr
     const float* x_in;                  // reference ABI: embedded tokens fp32 [nb][d] on the device, else nullptr
     int text_offset;                    // used when d_pos == nullptr
+    int no_vocab;                       // stop after the last layer (prompt positions whose logits nobody reads)
     unsigned* barrier;                  // [0] grid-barrier arrivals, [1] CTAs that have left the kernel
     unsigned* seq;                      // launch sequence number (device memory; the kernel increments it)
     long long dbg_delay;                // experiment: cycles the producer waits before it starts streaming

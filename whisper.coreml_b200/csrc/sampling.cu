@@ -19,7 +19,7 @@ void sample_partial(const SampleArgs& a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) beam_update_kernel(const BeamUpdateArgs a) {
     __shared__ int stage[DEC_MAX_BEAMS * DEC_TOK_LD];
-    beam_update_body<256>(a, stage, threadIdx.x, BlockSync());
+    beam_update_body<256, false>(a, stage, nullptr, threadIdx.x, BlockSync());
 }
 
 void beam_update(const BeamUpdateArgs& a, cudaStream_t s) {

@@ -52,7 +52,6 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
     __shared__ Rules rules;
     __shared__ int s_last;
     __shared__ float red_m[8], red_s[8];
-    __shared__ float arg_v[8]; __shared__ int arg_i[8]; __shared__ int s_pick;
     const DecodeState& st = *a.st;
     if (st.done) return;
     const int lane = tid & 31, warp = tid >> 5;
@@ -104,7 +103,9 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
         for (int w = 1; w < SP_WARPS; ++w) online_merge(m, s, red_m[w], red_s[w]);
         a.part->m[b][chunk] = m; a.part->s[b][chunk] = s;
     }
-    // chunk-local top-k by repeated block arg-max over the register-resident values (ties -> lowest index)
+    // chunk-local top-k (ties -> lowest index) in two levels: every warp extracts its own top-k from the register-resident
+    // values with shuffles only, then warp 0 merges the <= 8 * k survivors - one block barrier instead of two per rank
+    __shared__ float wv[8][SAMPLE_MAX_K]; __shared__ int wi[8][SAMPLE_MAX_K];
     unsigned taken = 0;
     for (int c = 0; c < a.k; ++c) {
         float bv = -INFINITY; int bi = 0x7fffffff;
@@ -118,24 +119,47 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
             const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        if (lane == 0) { arg_v[warp] = bv; arg_i[warp] = bi; }
-        sync();
-        if (tid == 0) {
-            for (int w = 1; w < SP_WARPS; ++w) if (arg_v[w] > bv || (arg_v[w] == bv && arg_i[w] < bi)) { bv = arg_v[w]; bi = arg_i[w]; }
-            a.part->topv[b][chunk][c] = bv; a.part->topi[b][chunk][c] = bi;
-            s_pick = bi;
+        if (lane == 0) { wv[warp][c] = bv; wi[warp][c] = bi; }
+        if (bi != 0x7fffffff && (bi - lo) % SP_THREADS == tid) taken |= 1u << ((bi - lo) / SP_THREADS);   // a picked slot never competes again
+    }
+    sync();
+    if (warp == 0) {
+        const int n = SP_WARPS * a.k;                      // <= 72 survivors, <= 3 per lane
+        float cv[3]; int ci[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const int q = lane + 32 * e;
+            cv[e] = -INFINITY; ci[e] = 0x7fffffff;
+            if (q < n) { cv[e] = wv[q / a.k][q % a.k]; ci[e] = wi[q / a.k][q % a.k]; }
         }
-        sync();
-        const int pick = s_pick;                           // a picked slot never competes again
-        if (pick != 0x7fffffff && (pick - lo) % SP_THREADS == tid) taken |= 1u << ((pick - lo) / SP_THREADS);
+        unsigned tk = 0;
+        for (int c = 0; c < a.k; ++c) {
+            float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+            for (int e = 0; e < 3; ++e)
+                if (!((tk >> e) & 1u) && (cv[e] > bv || (cv[e] == bv && ci[e] < bi))) { bv = cv[e]; bi = ci[e]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { a.part->topv[b][chunk][c] = bv; a.part->topi[b][chunk][c] = bi; }
+            if (bi != 0x7fffffff) {
+#pragma unroll
+                for (int e = 0; e < 3; ++e) if (ci[e] == bi) tk |= 1u << e;       // token indices are unique
+            }
+        }
     }
 }
 
 
 // `stage`: DEC_MAX_BEAMS * DEC_TOK_LD ints of shared scratch; `tid` in [0, NT); sync() as above.  Nothing here may live in
 // local memory (inside the persistent kernel a stack access is an L2 round trip): the sort keys are in shared memory.
-template <int NT, class Sync>
-__device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* stage, int tid, Sync sync) {
+// PRE: the caller has already copied the token rows into `stage` and the slot table into `stage2` (the persistent step kernel
+// stages them with cp.async; without an L1 a plain global load per element would be an L2 round trip each).
+template <int NT, bool PRE, class Sync>
+__device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* stage, int* stage2, int tid, Sync sync) {
+    const int* tok_src = PRE ? stage : a.tokens;
     __shared__ float sc[DEC_MAX_BEAMS * SAMPLE_MAX_K]; __shared__ int id[DEC_MAX_BEAMS * SAMPLE_MAX_K];
     __shared__ int nsrc[DEC_MAX_BEAMS], ntok[DEC_MAX_BEAMS];
     __shared__ float nsum[DEC_MAX_BEAMS];
@@ -165,25 +189,33 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
         // "if sum of probability over timestamps is above any other token, sample timestamp" (decoding.py:525-532)
         const bool mask_text = !st.without_timestamps && (lse_q - lse_all) > (mt - lse_all);
         const float lse = mask_text ? lse_q : lse_all;
-        // candidates: chunk c, rank r -> flat index c * k + r, spread over the lanes
-        const int ncand = SAMPLE_CHUNKS * a.k;
+        // candidates: chunk c, rank r -> flat index c * k + r, spread over the lanes and read ONCE into registers
+        const int ncand = SAMPLE_CHUNKS * a.k;             // <= 29 * 9 = 261 -> <= 9 per lane
+        float cv[9]; int ci[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) {
+            const int q = lane + 32 * e;
+            cv[e] = -INFINITY; ci[e] = 0x7fffffff;
+            if (q < ncand) {
+                const int ch = q / a.k, rk = q - ch * a.k;
+                if (!(mask_text && ch < SAMPLE_TEXT_CHUNKS)) { cv[e] = P.topv[warp][ch][rk]; ci[e] = P.topi[warp][ch][rk]; }
+            }
+        }
         unsigned taken = 0;
         for (int c = 0; c < a.k; ++c) {
             float bv = -INFINITY; int bi = 0x7fffffff;
-            for (int q = lane, e = 0; q < ncand; q += 32, ++e) {
-                const int ch = q / a.k, rk = q % a.k;
-                if ((taken >> e) & 1u) continue;
-                if (mask_text && ch < SAMPLE_TEXT_CHUNKS) continue;
-                const float v = P.topv[warp][ch][rk]; const int ix = P.topi[warp][ch][rk];
-                if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
-            }
+#pragma unroll
+            for (int e = 0; e < 9; ++e)
+                if (!((taken >> e) & 1u) && (cv[e] > bv || (cv[e] == bv && ci[e] < bi))) { bv = cv[e]; bi = ci[e]; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
             }
-            for (int q = lane, e = 0; q < ncand; q += 32, ++e)
-                if (P.topi[warp][q / a.k][q % a.k] == bi && !(mask_text && q / a.k < SAMPLE_TEXT_CHUNKS)) taken |= 1u << e;
+            if (bi != 0x7fffffff) {
+#pragma unroll
+                for (int e = 0; e < 9; ++e) if (ci[e] == bi) taken |= 1u << e;       // token indices are unique across chunks
+            }
             if (lane == 0) {
                 c_lp[warp * a.k + c] = bv - lse; c_tok[warp * a.k + c] = bi;
                 a.cand_lp[warp * a.k + c] = bv - lse; a.cand_tok[warp * a.k + c] = bi;
@@ -195,7 +227,7 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
     if (tid == 0) {
         int nfin_new = 0, done = 0;
         if (!st.beam_mode) {
-            const int tok = c_tok[0], last = a.tokens[L - 1];
+            const int tok = c_tok[0], last = tok_src[L - 1];
             nsrc[0] = 0;
             ntok[0] = last == a.eot ? a.eot : tok;
             nsum[0] = st.sum_lp[0] + (last == a.eot ? 0.f : c_lp[0]);
@@ -226,25 +258,30 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
     const int max_cand = nb;
     int nfin = st.n_finished;
     for (int f = 0; f < s_nfin_new && nfin < max_cand; ++f, ++nfin) {
-        const int* src = a.tokens + fin_src[f] * DEC_TOK_LD;
+        const int* src = tok_src + fin_src[f] * DEC_TOK_LD;
         int* dst = a.fin_tokens + nfin * DEC_TOK_LD;
         for (int i = tid; i < L; i += NT) dst[i] = src[i];
         if (tid == 0) { dst[L] = a.eot; st.fin_len[nfin] = L + 1; st.fin_score[nfin] = fin_sc[f]; }
     }
     sync();
     // permute token histories and KV slot tables by source beam, append the new tokens
-    for (int i = tid; i < nb * DEC_TOK_LD; i += NT) stage[i] = a.tokens[i];
-    sync();
+    if (!PRE) {
+        for (int i = tid; i < nb * DEC_TOK_LD; i += NT) stage[i] = a.tokens[i];
+        sync();
+    }
     for (int i = tid; i < nb * L; i += NT) {
         const int bb = i / L, p = i % L;
         a.tokens[bb * DEC_TOK_LD + p] = stage[nsrc[bb] * DEC_TOK_LD + p];
     }
-    sync();
-    for (int i = tid; i < nb * 448; i += NT) stage[i] = a.table[i];
-    sync();
+    const int* tab_src = PRE ? stage2 : stage;
+    if (!PRE) {
+        sync();
+        for (int i = tid; i < nb * 448; i += NT) stage[i] = a.table[i];
+        sync();
+    }
     for (int i = tid; i < nb * L; i += NT) {
         const int bb = i / L, p = i % L;
-        if (p < 448) a.table[bb * 448 + p] = stage[nsrc[bb] * 448 + p];
+        if (p < 448) a.table[bb * 448 + p] = tab_src[nsrc[bb] * 448 + p];
     }
     if (tid < nb) { a.tokens[tid * DEC_TOK_LD + L] = ntok[tid]; st.sum_lp[tid] = nsum[tid]; }
     sync();
