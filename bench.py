@@ -152,7 +152,8 @@ def main():
                 f"(randn*0.1, seed 1+rank) = {n_windows} fixed 30-s windows per GPU per step, sample_len={a.sample_len}, "
                 f"condition_on_previous_text=False, temperature 0")
     config = {"workload": workload, "windows_per_step_per_gpu": n_windows, "beam_size": a.beam, "sample_len": a.sample_len,
-              "word_timestamps": bool(a.word_timestamps), "l2": "working set (>2 GB of weights per step) exceeds the 126 MB L2"}
+              "word_timestamps": bool(a.word_timestamps), "l2": "working set (>2 GB of weights per step) exceeds the 126 MB L2",
+              "decode_lanes": "independent windows decode concurrently, 2 lanes (B200_DECODE_LANES)"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -160,7 +161,7 @@ def main():
         _, _, ckpt_path = weights_folder(a.model, a.seed)
         vals = []
         for i in range(a.warmup + a.steps):
-            r = cpu_reference(dims, ckpt_path, dims.n_mels, a.sample_len, a.beam, 17, audio_seconds, n_windows)
+            r = cpu_reference(dims, ckpt_path, dims.n_mels, a.sample_len, a.beam, min(65, a.sample_len), audio_seconds, n_windows)
             if i >= a.warmup:
                 vals.append(r)
         v = statistics.mean(x["rtfx"] for x in vals)
@@ -250,9 +251,17 @@ def main():
         t_mean = sum(n_init + (x - 1) / 2.0 for x in res["decode_steps"]) / len(res["decode_steps"])
         by = decoder1_bytes(dims, max(a.beam, 1), t_mean)
         ach = by / (per_step_ms * 1e-3) / 1e9
-        out["roofline"] = {"kernel": "decoder1 step (LN+GEMV x7/layer, self/cross attention, vocab projection, sampling)",
-                           "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
-                           "peak_source": which, "bytes_per_step": by, "us_per_step": per_step_ms * 1e3, "steps": dec_steps}
+        lanes = min(2, n_windows) if os.environ.get("B200_DECODE_LANES", "2") != "1" else 1
+        out["roofline"] = {"kernel": "decoder_mega_kernel: one persistent launch per decoder1 token step (LN + 7 GEMVs per layer, self / "
+                                     "cross attention, vocabulary projection) + the 2 sampling kernels that follow it",
+                           "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                           # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_decoder_mega_v2_ncu_full.csv (t ~ 10)
+                           "traffic": 356.2e6,
+                           "peak_source": which, "bytes_per_step": by, "us_per_step": per_step_ms * 1e3, "steps": dec_steps,
+                           "lanes": lanes,
+                           "note": f"algorithmic bytes of one token step of one window (SURVEY 8d formula at the mean text_offset) divided by "
+                                   f"the CUDA-event time of the whole decoder1 loop per window-step, sampling kernels and launch gaps included; "
+                                   f"{lanes} windows decode concurrently on disjoint SM halves, so this is the aggregate rate of {lanes} step kernels"}
     enc_ms = stages["encoder"] / a.steps / n_windows
     if enc_ms > 0:
         fl = encoder_flops(dims)
@@ -260,7 +269,7 @@ def main():
                                    "frac": fl / (enc_ms * 1e-3) / 1e12 / tf, "flops_per_window": fl, "ms_per_window": enc_ms,
                                    "peak_source": which + " (sustained cuBLAS bf16)"}
     if a.cpu_baseline and world == 1:
-        r = cpu_reference(dims, ckpt_path, dims.n_mels, a.sample_len, a.beam, 9, audio_seconds, n_windows)
+        r = cpu_reference(dims, ckpt_path, dims.n_mels, a.sample_len, a.beam, a.sample_len, audio_seconds, n_windows)   # ~10 s: one full window
         out["cpu_baseline"] = {"value": r["rtfx"], "unit": "audio_s/wall_s", "cores": r["cores"], "kind": "port",
                                "sample": f"1 of {n_windows} windows: mel + encoder + crossKV + decoder256 x{a.beam} + {r['steps_timed']-1} "
                                          f"decoder1 steps (fp32 torch CPU oracle), extrapolated to {r['steps_extrapolated']} steps x {n_windows} windows",
