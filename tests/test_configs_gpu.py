@@ -1,0 +1,91 @@
+"""The BASELINE.json configurations as parity cases (the bench measures only configs[3] at full length):
+  configs[1]  base, beam_size=5, language en, one 30-s window
+  configs[2]  small, word_timestamps=True, fixed 30-s windows of a longer clip (2 windows here)
+  configs[3]  large-v3-turbo dims (32 enc / 4 dec layers, 128 mels), beam_size=5, encoder + crossKV + decoder256 + decoder1
+Each compares the CUDA path (through the C ABI) with the CPU oracle on the same seeded weights and audio.
+Tolerances (north_star): encoder / logits relative error <= 2e-2, token sequences >= 99% identical, DTW bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import audio as oa, decoding as od, model as om, synth, timing as ot
+from tests._util import exported, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _agreement(a, b):
+    return sum(x == y for x, y in zip(a, b)) / max(len(a), len(b), 1)
+
+
+def _model(name, seed=0, scale=1.0):
+    from whisper_b200.model import ModelDimensions, WhisperB200
+    dims, ckpt, folder = exported(name, seed, scale)
+    return dims, ckpt, WhisperB200(ModelDimensions(**dims.as_dict()), folder).load()
+
+
+def test_config1_base_beam5_single_window():
+    from whisper_b200.decoding import DecodingOptions, decode
+    dims, ckpt, m = _model("base")
+    mel = oa.log_mel_spectrogram(synth.noise_audio(1, 480000), dims.n_mels, padding=480000)[:, :3000].contiguous()
+    m.encode_windows(mel.cuda(), [0])
+    got = decode(m, DecodingOptions(beam_size=5, sample_len=32, language="en"), window=0)
+    want = od.decode_window(om.OracleModel(dims, ckpt), mel, od.Specials.load(dims.n_vocab), od.Options(sample_len=32, beam_size=5))
+    assert _agreement(got.tokens, want.tokens) >= 0.99, (got.tokens, want.tokens)
+    assert got.steps == want.steps
+    assert abs(got.avg_logprob - want.avg_logprob) <= 2e-2 * max(1.0, abs(want.avg_logprob))
+    m.close()
+
+
+def test_config2_small_word_timestamps_two_windows():
+    from whisper_b200.transcribe import transcribe
+    dims, ckpt, m = _model("small")                    # reference-default init (near-uniform logits would let bf16 flip near-ties)
+    audio = torch.cat([synth.noise_audio(1, 480000), synth.noise_audio(2, 480000)])
+    res = transcribe(m, audio, beam_size=5, word_timestamps=True, sample_len=20)
+    assert res["windows"] == 2 and res["seeks"] == [0, 3000]
+    orc = om.OracleModel(dims, ckpt)
+    sp = od.Specials.load(dims.n_vocab)
+    mel = oa.log_mel_spectrogram(audio, dims.n_mels, padding=480000)
+    for w, seek in enumerate(res["seeks"]):
+        want = od.decode_window(orc, mel[:, seek:seek + 3000].contiguous(), sp, od.Options(sample_len=20, beam_size=5))
+        segs = [s for s in res["segments"] if s["seek"] == seek]
+        got = [t for s in segs for t in s["tokens"]]
+        assert _agreement(got, want.tokens) >= 0.99, (w, got, want.tokens)
+        for s in segs:                                 # timing.py:268-376: one word entry per text token, times inside the window
+            text = [t for t in s["tokens"] if t < sp.eot]
+            assert len(s["words"]) == len(text)
+            t0 = seek * 0.01
+            prev = t0
+            for wd in s["words"]:
+                assert t0 - 1e-6 <= wd["start"] <= wd["end"] <= t0 + 30.0 + 1e-6
+                assert wd["start"] >= prev - 1e-6       # DTW paths are monotone
+                prev = wd["start"]
+                assert 0.0 <= wd["probability"] <= 1.0
+    m.close()
+
+
+def test_config3_turbo_split_stages():
+    """turbo dims: encoder output, cross K/V and an 8-step beam-5 decode (prompt + decoder1 steps) against the oracle."""
+    import ctypes
+    from whisper_b200 import _lib
+    from whisper_b200.decoding import DecodingOptions, decode
+    dims, ckpt, m = _model("turbo")
+    orc = om.OracleModel(dims, ckpt)
+    mel = oa.log_mel_spectrogram(synth.noise_audio(1, 480000), dims.n_mels, padding=480000)[:, :3000].contiguous()
+    m.encode_windows(mel.cuda(), [0])
+    d, Ld, H = dims.n_text_state, dims.n_text_layer, dims.n_text_head
+    xa = torch.empty(1500, d)
+    m.lib.b200TestGetXa(ctypes.cast(xa.data_ptr(), _lib.f32p), 0)
+    xa_ref = orc.encode(mel)
+    assert rel(xa, xa_ref) < 2e-2, rel(xa, xa_ref)
+    ck = torch.empty(Ld, H, 64, 1500); cv = torch.empty(Ld, H, 1500, 64)
+    m.lib.b200TestGetCrossKV(ctypes.cast(ck.data_ptr(), _lib.f32p), ctypes.cast(cv.data_ptr(), _lib.f32p), 0)
+    ck_ref, cv_ref = om.cross_kv(orc.w, dims, xa_ref)
+    assert rel(ck, ck_ref) < 2e-2 and rel(cv, cv_ref) < 2e-2
+    sp = od.Specials.load(dims.n_vocab)
+    for beam in (None, 5):
+        got = decode(m, DecodingOptions(beam_size=beam, sample_len=8), window=0)
+        want = od.decode_window(orc, mel, sp, od.Options(sample_len=8, beam_size=beam))
+        assert _agreement(got.tokens, want.tokens) >= 0.99, (beam, got.tokens, want.tokens)
+        assert abs(got.sum_logprob - want.sum_logprob) <= 2e-2 * max(1.0, abs(want.sum_logprob)), (got.sum_logprob, want.sum_logprob)
+    m.close()
