@@ -52,3 +52,12 @@ for base, nm in ((200, "L0.qkv LN (embed)"), (220, "L0.mlp1 LN (LL)")):
         if prev is not None: out.append(f"{names[k]}+{v - prev}")
         prev = v
     print(nm, "CTA", c, "cycles:", " ".join(out))
+pn = {300: "sp.enter", 301: "sp.rules", 302: "sp.values+warp reduce", 303: "sp.block reduce", 304: "sp.warp top-k", 305: "sp.merge", 310: "bu.enter", 311: "bu.candidates", 312: "bu.sort (thread 0)", 313: "bu.finished pool", 314: "bu.permute"}
+prev = None
+out = []
+for k in sorted(pn):
+    v = T[0, k] if k < LD else 0
+    if v == 0: continue
+    if prev is not None: out.append(f"{pn[k]}+{v - prev}")
+    prev = v
+if out: print("tail probes (CTA 0, cycles):", " ".join(out))

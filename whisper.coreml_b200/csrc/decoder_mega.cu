@@ -131,7 +131,7 @@ __device__ __forceinline__ void ll_load2x5(LL5& r, const uint2* p0, const uint2*
 // Reads an LL matrix of n_rows x row_items 16-byte items (2 words each) and hands every item to f(row, c, word0, word1).
 // A thread owns items c = tid + 128 i (i < 5) of every row; two rows (10 loads) are in flight per round, and nothing is
 // stored before the round's loads have all returned.  Items beyond row_items / n_rows re-read item 0 and are dropped.
-constexpr int MG_IPR = 5;                            // items per row and thread (row_items <= 640)
+constexpr int MG_IPR = 5, MG_LN_ROWS = 3;                            // items per row and thread (row_items <= 640)
 template <class F>
 __device__ __forceinline__ void ll_read_rows(const uint2* __restrict__ src, uint32_t epoch, int n_rows, int row_items, int tid, int where, F f) {
     bool v[MG_IPR];
@@ -348,38 +348,38 @@ __device__ __forceinline__ void prologue_ln(const MegaSmem& sm, Ring& ring, cons
         ll_wait_sentinels(x_ll, epoch, d, 16, false, a.nb, tid, 12);       // written by 16-column GEMV tiles
         dbg.cyc(db + 2);
 #pragma unroll 1
-        for (int r0 = 0; r0 < a.nb; r0 += 2) {                             // two rows (ten loads) per round
-            const bool two = r0 + 1 < a.nb;
-            const uint2* pa = x_ll + 2L * r0 * row_items;
-            const uint2* pb = two ? pa + 2L * row_items : pa;
-            LL5 ra, rb;
+        for (int r0 = 0; r0 < a.nb; r0 += MG_LN_ROWS) {                    // MG_LN_ROWS rows (5 loads each) in flight per round
+            LL5 rr[MG_LN_ROWS];
+            const uint2* pr[MG_LN_ROWS];
+#pragma unroll
+            for (int q = 0; q < MG_LN_ROWS; ++q) pr[q] = x_ll + 2L * min(r0 + q, a.nb - 1) * row_items;     // rows past nb re-read the last row
             unsigned spins = 0;
             bool ok;
             do {
-                ll_load2x5(ra, pa + 2 * cc[0], pa + 2 * cc[1], pa + 2 * cc[2], pa + 2 * cc[3], pa + 2 * cc[4]);
-                ll_load2x5(rb, pb + 2 * cc[0], pb + 2 * cc[1], pb + 2 * cc[2], pb + 2 * cc[3], pb + 2 * cc[4]);
+#pragma unroll
+                for (int q = 0; q < MG_LN_ROWS; ++q) ll_load2x5(rr[q], pr[q] + 2 * cc[0], pr[q] + 2 * cc[1], pr[q] + 2 * cc[2], pr[q] + 2 * cc[3], pr[q] + 2 * cc[4]);
                 ok = true;
 #pragma unroll
-                for (int i = 0; i < MG_IPR; ++i) ok = ok & ll_ok(ra.w[i][0], epoch) & ll_ok(ra.w[i][1], epoch) & ll_ok(rb.w[i][0], epoch) & ll_ok(rb.w[i][1], epoch);
+                for (int q = 0; q < MG_LN_ROWS; ++q)
+#pragma unroll
+                    for (int i = 0; i < MG_IPR; ++i) ok = ok & ll_ok(rr[q].w[i][0], epoch) & ll_ok(rr[q].w[i][1], epoch);
                 if (!ok) ll_backoff(spins, 2);
             } while (!ok);
-            float2* da = reinterpret_cast<float2*>(sm.xs + (long)r0 * sm.ldx + d);
-            float2* db2 = reinterpret_cast<float2*>(sm.xs + (long)(r0 + 1) * sm.ldx + d);
-            float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll
-            for (int i = 0; i < MG_IPR; ++i)
-                if (v[i]) {
-                    const float x = __uint_as_float((uint32_t)ra.w[i][0]), y = __uint_as_float((uint32_t)ra.w[i][1]);
-                    da[cc[i]] = make_float2(x, y);
-                    a1 += x + y; a2 = fmaf(x, x, fmaf(y, y, a2));
-                    if (two) {
-                        const float z = __uint_as_float((uint32_t)rb.w[i][0]), w = __uint_as_float((uint32_t)rb.w[i][1]);
-                        db2[cc[i]] = make_float2(z, w);
-                        b1 += z + w; b2 = fmaf(z, z, fmaf(w, w, b2));
-                    }
+            for (int q = 0; q < MG_LN_ROWS; ++q) {
+                if (r0 + q < a.nb) {                                   // warp uniform
+                    float2* dst = reinterpret_cast<float2*>(sm.xs + (long)(r0 + q) * sm.ldx + d);
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < MG_IPR; ++i)
+                        if (v[i]) {
+                            const float x = __uint_as_float((uint32_t)rr[q].w[i][0]), y = __uint_as_float((uint32_t)rr[q].w[i][1]);
+                            dst[cc[i]] = make_float2(x, y);
+                            s1 += x + y; s2 = fmaf(x, x, fmaf(y, y, s2));
+                        }
+                    row_done(r0 + q, s1, s2);
                 }
-            row_done(r0, a1, a2);
-            if (two) row_done(r0 + 1, b1, b2);
+            }
         }
     }
     dbg.cyc(db + 11);
@@ -844,6 +844,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decoder_mega_kernel(const __gri
         // Everything the two phases read is first copied into shared memory with 4-byte cp.async (one L2 round trip, all
         // in flight together); the generic bodies of sampling_dev.cuh then run against those copies.
         uint8_t* scratch = reinterpret_cast<uint8_t*>(sm.xs);
+#ifdef B200_PROBES
+        if (tid == 0 && cta == 0) g_probe = a.dbg;                     // experiments: cycle probes of CTA 0 in the bodies
+#endif
         const int tb = a.spec.timestamp_begin, V = a.spec.n_vocab;
         for (int u = cta; u < SAMPLE_CHUNKS * a.nb; u += nctas) {
             const int chunk = u % SAMPLE_CHUNKS, b = u / SAMPLE_CHUNKS;

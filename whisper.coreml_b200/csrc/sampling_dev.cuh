@@ -42,6 +42,15 @@ __device__ __forceinline__ void online_merge(float& m, float& s, float m2, float
     m = M;
 }
 
+// cycle probes for experiments with the in-kernel sampling tail (compile with -DB200_PROBES): thread 0 of block 0 stores
+// clock64() at g_probe[idx]; tools/step_timeline.py prints them
+#ifdef B200_PROBES
+__device__ unsigned long long* g_probe = nullptr;
+__device__ __forceinline__ void probe(int idx, int tid) { if (g_probe && tid == 0 && blockIdx.x == 0) g_probe[idx] = (unsigned long long)clock64(); }
+#else
+__device__ __forceinline__ void probe(int, int) {}
+#endif
+
 constexpr int SP_CHUNK_MAX = 2048;                     // >= largest chunk (1799 text / 1502 timestamp tokens)
 
 // One (chunk, beam) unit; `tid` in [0, SP_THREADS); sync() is a barrier over exactly those SP_THREADS threads (256 in the
@@ -59,6 +68,7 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
     const int V = sp.n_vocab, tb = sp.timestamp_begin;
     const int* seq = a.tokens + b * DEC_TOK_LD + st.sample_begin;
     const int n = st.L - st.sample_begin;
+    probe(300, tid);
     if (tid == 0) s_last = -1;
     sync();
     int last = -1;
@@ -78,6 +88,7 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
         rules = r;
     }
     sync();
+    probe(301, tid);
     const Rules r = rules;
     int lo, hi;
     if (chunk < SAMPLE_TEXT_CHUNKS) {
@@ -85,18 +96,44 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
         lo = chunk * per; hi = min(tb, lo + per);
     } else { lo = tb; hi = V; }
     const float* x = a.logits + (long)b * a.ld_logits;
+    // Three passes so that nothing in the per-token work is a dependent chain: (1) all loads, (2) the filters with the
+    // thread-uniform state hoisted into registers, (3) max, then the sum of exponentials.
     float val[SP_PER_THREAD];
-    float m = -INFINITY, s = 0.f;
+    unsigned supm = 0;
 #pragma unroll
     for (int e = 0; e < SP_PER_THREAD; ++e) {
         const int v = lo + e * SP_THREADS + tid;
-        float t = -INFINITY;
-        if (v < hi && !is_masked(v, sp, st, r)) t = x[v];
-        val[e] = t;
-        online_add(m, s, t);
+        val[e] = -INFINITY;
+        if (v < hi) { val[e] = x[v]; supm |= (unsigned)(sp.d_suppress[v] != 0) << e; }
+    }
+    {
+        const int eot = sp.eot, no_ts = sp.no_timestamps, b0 = sp.blank[0], b1 = sp.blank[1], b2 = sp.blank[2], b3 = sp.blank[3];
+        const bool blank_rule = r.at_begin && st.suppress_blank, ts_rules = !st.without_timestamps;
+        const int max_init = st.max_initial_ts;
+#pragma unroll
+        for (int e = 0; e < SP_PER_THREAD; ++e) {
+            const int v = lo + e * SP_THREADS + tid;
+            bool masked = v >= hi || ((supm >> e) & 1u);                                             // SuppressTokens (:460-465)
+            masked |= blank_rule && (v == eot || v == b0 || v == b1 || v == b2 || v == b3);           // SuppressBlank (:450-457)
+            if (ts_rules) {                                                                           // ApplyTimestampRules (:468-523)
+                masked |= v == no_ts;
+                if (r.last_ts) masked |= r.penult_ts ? v >= tb : v < eot;
+                masked |= r.last_stamp >= 0 && v >= tb && v < r.lim;
+                if (r.at_begin) masked |= v < tb || (max_init >= 0 && v > tb + max_init);
+            }
+            if (masked) val[e] = -INFINITY;
+        }
+    }
+    float m = -INFINITY, s = 0.f;
+#pragma unroll
+    for (int e = 0; e < SP_PER_THREAD; ++e) m = fmaxf(m, val[e]);
+    if (m != -INFINITY) {
+#pragma unroll
+        for (int e = 0; e < SP_PER_THREAD; ++e) s += __expf(val[e] - m);                             // exp(-inf) = 0 for the masked tokens
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) online_merge(m, s, __shfl_xor_sync(0xffffffffu, m, o), __shfl_xor_sync(0xffffffffu, s, o));
+    probe(302, tid);
     if (lane == 0) { red_m[warp] = m; red_s[warp] = s; }
     sync();
     if (tid == 0) {
@@ -106,6 +143,7 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
     // chunk-local top-k (ties -> lowest index) in two levels: every warp extracts its own top-k from the register-resident
     // values with shuffles only, then warp 0 merges the <= 8 * k survivors - one block barrier instead of two per rank
     __shared__ float wv[8][SAMPLE_MAX_K]; __shared__ int wi[8][SAMPLE_MAX_K];
+    probe(303, tid);
     unsigned taken = 0;
     for (int c = 0; c < a.k; ++c) {
         float bv = -INFINITY; int bi = 0x7fffffff;
@@ -123,6 +161,7 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
         if (bi != 0x7fffffff && (bi - lo) % SP_THREADS == tid) taken |= 1u << ((bi - lo) / SP_THREADS);   // a picked slot never competes again
     }
     sync();
+    probe(304, tid);
     if (warp == 0) {
         const int n = SP_WARPS * a.k;                      // <= 72 survivors, <= 3 per lane
         float cv[3]; int ci[3];
@@ -150,6 +189,7 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
             }
         }
     }
+    probe(305, tid);
 }
 
 
@@ -169,6 +209,7 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
     DecodeState& st = *a.st;
     if (st.done) return;
     const int warp = tid >> 5, lane = tid & 31, nb = a.nb, L = st.L;
+    probe(310, tid);
     // ---- warp b: log-softmax normaliser and top-k of beam b from the chunk partials ----------------------
     for (int bw = warp; bw < nb; bw += NT / 32) {
         const int warp = bw;                                 // one warp per beam
@@ -189,17 +230,13 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
         // "if sum of probability over timestamps is above any other token, sample timestamp" (decoding.py:525-532)
         const bool mask_text = !st.without_timestamps && (lse_q - lse_all) > (mt - lse_all);
         const float lse = mask_text ? lse_q : lse_all;
-        // candidates: chunk c, rank r -> flat index c * k + r, spread over the lanes and read ONCE into registers
-        const int ncand = SAMPLE_CHUNKS * a.k;             // <= 29 * 9 = 261 -> <= 9 per lane
+        // candidates: lane c holds the k survivors of chunk c, read ONCE into registers (no index arithmetic)
         float cv[9]; int ci[9];
+        const bool mine = lane < SAMPLE_CHUNKS && !(mask_text && lane < SAMPLE_TEXT_CHUNKS);
 #pragma unroll
         for (int e = 0; e < 9; ++e) {
-            const int q = lane + 32 * e;
             cv[e] = -INFINITY; ci[e] = 0x7fffffff;
-            if (q < ncand) {
-                const int ch = q / a.k, rk = q - ch * a.k;
-                if (!(mask_text && ch < SAMPLE_TEXT_CHUNKS)) { cv[e] = P.topv[warp][ch][rk]; ci[e] = P.topi[warp][ch][rk]; }
-            }
+            if (mine && e < a.k) { cv[e] = P.topv[warp][lane][e]; ci[e] = P.topi[warp][lane][e]; }
         }
         unsigned taken = 0;
         for (int c = 0; c < a.k; ++c) {
@@ -223,7 +260,27 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
         }
     }
     sync();
+    probe(311, tid);
     if (!a.update) return;
+    if (st.beam_mode) {
+        // stable descending sort of the <= 72 cumulative scores by rank counting: thread i places candidate i (the Python
+        // `sorted(..., reverse=True)` of decoding.py:377 keeps equal keys in their original order)
+        __shared__ float key[DEC_MAX_BEAMS * SAMPLE_MAX_K];
+        const int nsb = st.step == 0 ? 1 : nb, n = nsb * a.k;
+        float mykey = 0.f;
+        if (tid < n) {
+            mykey = st.sum_lp[tid / a.k] + c_lp[tid];
+            if (!(mykey == mykey)) mykey = -INFINITY;        // NaN (-inf - -inf) sorts last
+            key[tid] = mykey;
+        }
+        sync();
+        if (tid < n) {
+            int rank = 0;
+            for (int q = 0; q < n; ++q) { const float o = key[q]; rank += (o > mykey || (o == mykey && q < tid)) ? 1 : 0; }
+            sc[rank] = mykey; id[rank] = tid;
+        }
+        sync();
+    }
     if (tid == 0) {
         int nfin_new = 0, done = 0;
         if (!st.beam_mode) {
@@ -234,15 +291,7 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
             done = ntok[0] == a.eot;
         } else {
             const int nsb = st.step == 0 ? 1 : nb;      // identical prefixes at step 0 collapse to one key set (:366-373)
-            const int n = nsb * a.k;
-            for (int j = 0; j < nsb; ++j)
-                for (int c = 0; c < a.k; ++c) { sc[j * a.k + c] = st.sum_lp[j] + c_lp[j * a.k + c]; id[j * a.k + c] = j * a.k + c; }
-            for (int i = 1; i < n; ++i) {                // stable insertion sort, descending (:377)
-                const float s = sc[i]; const int d = id[i];
-                int p = i - 1;
-                while (p >= 0 && sc[p] < s) { sc[p + 1] = sc[p]; id[p + 1] = id[p]; --p; }
-                sc[p + 1] = s; id[p + 1] = d;
-            }
+            const int n = nsb * a.k;                     // sc / id were ranked by all threads above (stable, descending, :377)
             int cnt = 0;
             for (int i = 0; i < n && cnt < nb; ++i) {
                 const int j = id[i] / a.k, tok = c_tok[id[i]];
@@ -254,6 +303,7 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
         s_nfin_new = nfin_new; s_done = done;
     }
     sync();
+    probe(312, tid);
     // finished pool: at most max_candidates (= nb, patience 1) sequences, best first (:396-402)
     const int max_cand = nb;
     int nfin = st.n_finished;
@@ -264,6 +314,7 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
         if (tid == 0) { dst[L] = a.eot; st.fin_len[nfin] = L + 1; st.fin_score[nfin] = fin_sc[f]; }
     }
     sync();
+    probe(313, tid);
     // permute token histories and KV slot tables by source beam, append the new tokens
     if (!PRE) {
         for (int i = tid; i < nb * DEC_TOK_LD; i += NT) stage[i] = a.tokens[i];
@@ -284,6 +335,7 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
         if (p < 448) a.table[bb * 448 + p] = tab_src[nsrc[bb] * 448 + p];
     }
     if (tid < nb) { a.tokens[tid * DEC_TOK_LD + L] = ntok[tid]; st.sum_lp[tid] = nsum[tid]; }
+    probe(314, tid);
     sync();
     if (tid == 0) {
         st.n_finished = nfin;
