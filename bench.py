@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--word-timestamps", action="store_true")
     ap.add_argument("--window-batch", type=int, default=8)
     ap.add_argument("--cpu-baseline", type=int, default=1, help="time the oracle port on host cores (N=1 only)")
+    ap.add_argument("--long-clip", type=float, default=4.0, help="minutes of a second, longer clip reported as long_clip (0 = skip; N=1 only)")
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
 
@@ -153,7 +154,7 @@ def main():
                 f"condition_on_previous_text=False, temperature 0")
     config = {"workload": workload, "windows_per_step_per_gpu": n_windows, "beam_size": a.beam, "sample_len": a.sample_len,
               "word_timestamps": bool(a.word_timestamps), "l2": "working set (>2 GB of weights per step) exceeds the 126 MB L2",
-              "decode_lanes": "independent windows decode concurrently, 2 lanes (B200_DECODE_LANES)"}
+              "decode_lanes": "independent windows decode concurrently, one lane per window up to 8 (B200_DECODE_LANES)"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -251,7 +252,7 @@ def main():
         t_mean = sum(n_init + (x - 1) / 2.0 for x in res["decode_steps"]) / len(res["decode_steps"])
         by = decoder1_bytes(dims, max(a.beam, 1), t_mean)
         ach = by / (per_step_ms * 1e-3) / 1e9
-        lanes = min(2, n_windows) if os.environ.get("B200_DECODE_LANES", "2") != "1" else 1
+        lanes = min(int(os.environ.get("B200_DECODE_LANES", "8")), 8, n_windows)
         out["roofline"] = {"kernel": "decoder_mega_kernel: one persistent launch per decoder1 token step (LN + 7 GEMVs per layer, self / "
                                      "cross attention, vocabulary projection) + the 2 sampling kernels that follow it",
                            "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
@@ -268,6 +269,23 @@ def main():
         out["encoder_roofline"] = {"bound": "tensor", "achieved": fl / (enc_ms * 1e-3) / 1e12, "peak": tf, "unit": "TFLOP/s",
                                    "frac": fl / (enc_ms * 1e-3) / 1e12 / tf, "flops_per_window": fl, "ms_per_window": enc_ms,
                                    "peak_source": which + " (sustained cuBLAS bf16)"}
+    if world == 1 and a.long_clip > 0:
+        # the same path on a longer clip: more independent windows -> more concurrent decode lanes (not the headline workload)
+        nl = int(a.long_clip * 60 * 16000)
+        long_audio = synth.noise_audio(101, nl).cuda()
+        transcribe(model, long_audio, **kw)
+        ms_l, _, res_l, _, st_l = timed(long_audio, 2)
+        wl = (nl + 480000 - 1) // 480000
+        ds = sum(max(x - 1, 0) for x in res_l["decode_steps"])
+        t_mean_l = sum(len(model.specials.sot_sequence) + (x - 1) / 2.0 for x in res_l["decode_steps"]) / len(res_l["decode_steps"])
+        by_l = decoder1_bytes(dims, max(a.beam, 1), t_mean_l)
+        ach_l = by_l / (st_l["decoder1"] / 2 / ds * 1e-3) / 1e9 if ds else 0.0
+        out["long_clip"] = {"minutes": a.long_clip, "windows_per_step": wl, "decode_lanes": min(8, wl), "value": (nl / 16000.0) * 2 / (ms_l / 1000.0),
+                            "unit": "audio_s/wall_s", "ms_per_step": ms_l / 2,
+                            "decoder1_hbm_gbs": ach_l, "decoder1_hbm_frac": ach_l / hbm,
+                            "encoder_tflops": encoder_flops(dims) / (st_l["encoder"] / 2 / wl * 1e-3) / 1e12,
+                            "note": "same transcribe() call on a longer clip (window_batch 8): algorithmic decoder1 bytes per window-step / "
+                                    "CUDA-event time of the decoder1 loop per window-step, aggregate over the concurrent lanes"}
     if a.cpu_baseline and world == 1:
         r = cpu_reference(dims, ckpt_path, dims.n_mels, a.sample_len, a.beam, a.sample_len, audio_seconds, n_windows)   # ~10 s: one full window
         out["cpu_baseline"] = {"value": r["rtfx"], "unit": "audio_s/wall_s", "cores": r["cores"], "kind": "port",

@@ -22,7 +22,7 @@ struct DecLayer {
     DecLinear qkv, attn_out, cross_q, cross_out, mlp1, mlp2;
 };
 
-constexpr int MAX_LANES = 2;              // window decodes that may run concurrently, each on its share of the SMs
+constexpr int MAX_LANES = 8;              // window decodes that may run concurrently, each on its share of the SMs
 
 struct State {
     int device = 0;
