@@ -20,6 +20,8 @@ LD = 640
 buf = np.zeros(256 * LD, dtype=np.uint64)
 n = m.lib.b200TestStepTimeline(0, buf.ctypes.data_as(ctypes.c_void_p), 256)
 T = buf[:n * LD].astype(np.int64).reshape(n, LD)
+T = T[T[:, 0] > 0]                      # CTAs that ran (B200_MEGA_CTAS < n_sms leaves the rest empty)
+n = T.shape[0]
 STAGES = ["qkv", "self_attn", "out_proj", "cross_q", "cross_attn", "cross_out", "mlp1", "mlp2"]
 n_stages = dims.n_text_layer * 8 + 1
 t0 = T[:, 0].min()

@@ -95,7 +95,7 @@ __device__ __forceinline__ void ll_load2(const uint2* p, u64& a, u64& b) {      
 __device__ __forceinline__ bool ll_ok(u64 v, uint32_t epoch) { return (uint32_t)(v >> 32) == epoch; }
 __device__ __forceinline__ void ll_backoff(unsigned& spins, int where) {
     if (++spins > MG_SPIN_LIMIT) mg_timeout(where);
-    __nanosleep(spins > 8 ? 128 : 32);
+    if (spins > 48) __nanosleep(64);                  // the first polls spin: __nanosleep's granularity is coarser than an L2 round trip
 }
 __device__ __forceinline__ uint32_t ll_wait1(const uint2* p, uint32_t epoch, int where) {
     u64 v;
