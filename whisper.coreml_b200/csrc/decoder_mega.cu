@@ -391,19 +391,29 @@ __device__ __forceinline__ void prologue_ln(const MegaSmem& sm, Ring& ring, cons
         const uint32_t gaddr = smem_u32(sm.ring + (size_t)ring.slot * MG_SLOT) + tid * 8;
         lds5(ga, gaddr); lds5(be, gaddr + d * 4);
         const float inv_d = 1.f / d;
+        // rows in groups of four: the staged items and the row statistics of a group are all fetched before any arithmetic
 #pragma unroll 1
-        for (int r = 0; r < a.nb; ++r) {
-            const float2 p0 = *reinterpret_cast<const float2*>(part + r * 2), p1 = *reinterpret_cast<const float2*>(part + (8 + r) * 2);
-            const float2 p2 = *reinterpret_cast<const float2*>(part + (16 + r) * 2), p3 = *reinterpret_cast<const float2*>(part + (24 + r) * 2);
-            const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * inv_d;
-            const float var = fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * inv_d - mean * mean, 0.f);
-            const float rstd = rsqrtf(var + 1e-5f);
-            float2 xv[MG_IPR];
-            lds5(xv, smem_u32(sm.xs + (long)r * sm.ldx + d) + tid * 8);
-            uint32_t* row = reinterpret_cast<uint32_t*>(sm.xs + (long)r * sm.ldx);
+        for (int r0 = 0; r0 < a.nb; r0 += 4) {
+            float2 xv[4][MG_IPR];
+            float mean[4], rstd[4];
 #pragma unroll
-            for (int i = 0; i < MG_IPR; ++i)
-                if (v[i]) row[cc[i]] = pack_bf16((xv[i].x - mean) * rstd * ga[i].x + be[i].x, (xv[i].y - mean) * rstd * ga[i].y + be[i].y);
+            for (int q = 0; q < 4; ++q) {
+                const int r = min(r0 + q, a.nb - 1);                    // (skipping the rows past nb here made ptxas spill)
+                lds5(xv[q], smem_u32(sm.xs + (long)r * sm.ldx + d) + tid * 8);
+                const float2 p0 = *reinterpret_cast<const float2*>(part + r * 2), p1 = *reinterpret_cast<const float2*>(part + (8 + r) * 2);
+                const float2 p2 = *reinterpret_cast<const float2*>(part + (16 + r) * 2), p3 = *reinterpret_cast<const float2*>(part + (24 + r) * 2);
+                mean[q] = ((p0.x + p1.x) + (p2.x + p3.x)) * inv_d;
+                rstd[q] = rsqrtf(fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * inv_d - mean[q] * mean[q], 0.f) + 1e-5f);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (r0 + q < a.nb) {
+                    uint32_t* row = reinterpret_cast<uint32_t*>(sm.xs + (long)(r0 + q) * sm.ldx);
+#pragma unroll
+                    for (int i = 0; i < MG_IPR; ++i)
+                        if (v[i]) row[cc[i]] = pack_bf16((xv[q][i].x - mean[q]) * rstd[q] * ga[i].x + be[i].x, (xv[q][i].y - mean[q]) * rstd[q] * ga[i].y + be[i].y);
+                }
+            }
         }
     }
     __syncwarp();
