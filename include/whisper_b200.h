@@ -162,6 +162,11 @@ long b200KernelLaunchCount();
  * tcgen05 GEMM and through the SIMT checker; device pointers, bf16 inputs. */
 void b200TestGemm(const void* dA, const void* dB, const float* dBias, void* dC, int M, int N, int K,
                   int out_fp32, int gelu, int use_simt);
+/* Force the GEMM tile configuration of every following tcgen05 GEMM: 0 automatic, 1 = 128x128, 2 = 128x256,
+ * 3 = CTA pair (cta_group::2) 256x256. */
+void b200TestGemmTile(int sel);
+/* Average device time in ms of `iters` back-to-back tcgen05 GEMMs; mode bits: 1 bias, 2 GELU, 4 fp32 output + fp32 residual. */
+float b200TestGemmTime(const void* dA, const void* dB, void* dC, int M, int N, int K, int mode, int iters);
 /* State read-back as fp32 HOST arrays in the reference's layouts: Xa (1500, d) of window w;
  * CK (Ld,H,64,1500) / CV (Ld,H,1500,64) of window w; logical KV cache rows (2Ld, bs, n_rows, d). */
 void b200TestGetXa(float* out, int w);

@@ -28,6 +28,30 @@ def test_gemm_tcgen05(lib, M, N, K, fp32, gelu, bias):
     assert _rel(C.float(), ref) < (1e-5 if fp32 else 4e-3)
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (3000, 1280, 1280), (1500, 3840, 1280), (3000, 5120, 1280), (3000, 1280, 5120), (777, 392, 192)])
+@pytest.mark.parametrize("fp32,gelu,bias", [(1, 0, 0), (0, 1, 1)])
+def test_gemm_cta_pair(lib, M, N, K, fp32, gelu, bias):
+    """The cta_group::2 (256 x 256 tile) kernel, forced for every shape, against torch fp32."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + 1)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g) if bias else None
+    C = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if fp32 else torch.bfloat16)
+    torch.cuda.synchronize()
+    lib.b200TestGemmTile(3)
+    try:
+        lib.b200TestGemm(A.data_ptr(), B.data_ptr(), b.data_ptr() if bias else None, C.data_ptr(), M, N, K, fp32, gelu, 0)
+    finally:
+        lib.b200TestGemmTile(0)
+    ref = A.float() @ B.float().t()
+    if bias:
+        ref = ref + b
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    assert not torch.isnan(C.float()).any()
+    assert _rel(C.float(), ref) < (1e-5 if fp32 else 4e-3)
+
+
 @pytest.mark.parametrize("n_tok,heads,batch", [(1500, 6, 1), (1500, 20, 2), (128, 2, 1), (77, 1, 3), (200, 4, 1)])
 def test_flash_attention_tcgen05(lib, n_tok, heads, batch):
     d = heads * 64

@@ -48,6 +48,8 @@ SIGNATURES = {
     "b200GetStageTimes": (None, [f32p, c_int]),
     # test hooks
     "b200TestGemm": (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "b200TestGemmTile": (None, [c_int]),
+    "b200TestGemmTime": (ctypes.c_float, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "b200TestGetXa": (None, [f32p, c_int]),
     "b200TestGetCrossKV": (None, [f32p, f32p, c_int]),
     "b200TestGetKV": (None, [f32p, c_int]),

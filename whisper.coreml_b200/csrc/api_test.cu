@@ -20,6 +20,37 @@ extern "C" void b200TestGemm(const void* dA, const void* dB, const float* dBias,
     B200_CHECK(cudaStreamSynchronize(0));
 }
 
+namespace b200 { extern int g_gemm_force; }
+extern "C" void b200TestGemmTile(int sel) { b200::g_gemm_force = sel; }
+
+// average device time (ms, CUDA events around `iters` back-to-back launches) of one GEMM configuration;
+// mode bits: 1 = bias, 2 = GELU, 4 = fp32 output with an fp32 residual added (else bf16 output)
+extern "C" float b200TestGemmTime(const void* dA, const void* dB, void* dC, int M, int N, int K, int mode, int iters) {
+    GemmParams p = gemm_plain((const bf16*)dA, (const bf16*)dB, dC, M, N, K);
+    float *bias = nullptr, *add = nullptr, *cf = nullptr;
+    if (mode & 1) { cudaMalloc(&bias, (size_t)N * 4); cudaMemset(bias, 0, (size_t)N * 4); p.bias = bias; }
+    p.gelu = (mode & 2) ? 1 : 0;
+    if (mode & 4) {
+        cudaMalloc(&add, (size_t)M * N * 4); cudaMemset(add, 0, (size_t)M * N * 4);
+        cudaMalloc(&cf, (size_t)M * N * 4);
+        p.add = add; p.add_rows = M; p.ld_add = N; p.C = cf; p.c_fp32 = 1;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) gemm_tcgen05(p, 0);
+    cudaEventRecord(e0, 0);
+    for (int i = 0; i < iters; ++i) gemm_tcgen05(p, 0);
+    cudaEventRecord(e1, 0);
+    B200_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (bias) cudaFree(bias);
+    if (add) cudaFree(add);
+    if (cf) cudaFree(cf);
+    return ms / (iters > 0 ? iters : 1);
+}
+
 // ---- state read-back hooks (tests only) ---------------------------------------------------------
 #include <vector>
 #include "state.cuh"

@@ -12,6 +12,8 @@
 // LayoutType 2), accumulation is fp32.
 #include "gemm.cuh"
 
+#include <stdlib.h>
+
 #include <map>
 #include <tuple>
 #include <vector>
@@ -39,9 +41,108 @@ struct GemmKernelArgs {
     long c_split_stride;
     bf16* C2; long c2_batch_stride; int c2_heads, c2_keys;
     int vec_ok;                 // output / residual rows are 16-byte aligned: 128-bit epilogue accesses allowed
+    int dbg_skip;               // experiments (B200_GEMM_SKIP): 1 = epilogue without global stores, 2 = no epilogue at all
 };
 
-template <int BLOCK_N, int STAGES>
+// Epilogue of one 128-row x BLOCK_N accumulator tile: the calling warp owns TMEM lanes [quad * 32, +32) (tmem_acc already
+// points at them) and the 32-column chunks half, half + 2, ... (the two warps of a quadrant write the two 64-byte halves of a
+// bf16 output line at about the same time); thread <-> output row t.  INFLIGHT chunks are loaded per tcgen05.wait::ld:
+// measured on the encoder's shapes, 1 is fastest (2 and 4 were 10-40 % slower: the bursts of stores that follow a larger
+// batch of loads compete with the next tile's operand reads for the shared-memory / L1 data path).
+template <int BLOCK_N, int INFLIGHT>
+__device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& g, uint32_t tmem_acc, int half, int lane, int n_blk, int b, int t,
+                                              bool row_ok, long c_row, const float* add_row) {
+    if (g.dbg_skip == 2) return;
+    constexpr int NSUB = BLOCK_N / 64;                  // 32-column sub-chunks of this warp
+    constexpr int NF = INFLIGHT < NSUB ? INFLIGHT : NSUB;
+#pragma unroll 1
+    for (int s0 = 0; s0 < NSUB; s0 += NF) {
+    uint32_t r[NF][32];
+#pragma unroll
+    for (int u = 0; u < NF; ++u) tmem_ld_32x32(tmem_acc + (half + 2 * (s0 + u)) * 32, r[u]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < NF; ++u) {
+        const int n0 = n_blk * BLOCK_N + (half + 2 * (s0 + u)) * 32;
+        if (n0 >= g.N) continue;                        // warp uniform
+        const bool full = g.vec_ok && n0 + 32 <= g.N;
+        float4 q[8];
+        if (add_row && full && row_ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q[i] = *reinterpret_cast<const float4*>(add_row + n0 + 4 * i);
+        }
+        // one coalesced bias load per sub-chunk (lane i holds column n0 + i), broadcast by shuffle
+        const float bv = (g.bias && n0 + lane < g.N) ? __ldg(g.bias + n0 + lane) : 0.f;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(r[u][i]);
+            if (g.bias) x += __shfl_sync(0xffffffffu, bv, i);
+            if (g.gelu) x = gelu_erf(x);
+            v[i] = x;
+        }
+        if (g.dbg_skip == 1) { float acc = 0.f; for (int i = 0; i < 32; ++i) acc += v[i]; if (acc == 1.2345e-30f) reinterpret_cast<float*>(g.C)[0] = acc; continue; }
+        if (!row_ok) continue;                          // rows past the batch: nothing to add or store (after the shuffles)
+        if (add_row) {
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { v[4 * i] += q[i].x; v[4 * i + 1] += q[i].y; v[4 * i + 2] += q[i].z; v[4 * i + 3] += q[i].w; }
+            } else {
+                for (int i = 0; i < 32 && n0 + i < g.N; ++i) v[i] += add_row[n0 + i];
+            }
+        }
+        if (g.C2) {                                     // fragment-major copy of cross K / V^T (see gemm.cuh)
+            const int grp = n0 >> 6, c0 = n0 & 63, j = t;
+            bf16* base = g.C2 + (long)b * g.c2_batch_stride + (long)grp * 64 * g.c2_keys;
+            if (((grp / g.c2_heads) & 1) == 0) {
+                bf16* dst = base + ((((j >> 4) * 2 + (c0 >> 5)) * 2 + ((j & 15) >> 3)) * 256) + (j & 7) * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 w;
+                    w.x = pack_bf16(v[i], v[i + 1]); w.y = pack_bf16(v[i + 2], v[i + 3]);
+                    w.z = pack_bf16(v[i + 4], v[i + 5]); w.w = pack_bf16(v[i + 6], v[i + 7]);
+                    *reinterpret_cast<uint4*>(dst + i) = w;
+                }
+            } else {
+                const int n_kc = g.c2_keys >> 5;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int c = c0 + i;
+                    base[((((c >> 4) * n_kc + (j >> 5)) * 2 + ((c & 15) >> 3)) * 256) + ((c & 7) * 4 + ((j & 31) >> 3)) * 8 + (j & 7)] =
+                        __float2bfloat16(v[i]);
+                }
+            }
+        }
+        // split mode: 64-column groups (heads) are c_split_stride elements apart
+        const long col_off = g.c_split ? (long)(n0 >> 6) * g.c_split_stride + (n0 & 63) : (long)n0;
+        if (g.c_fp32) {
+            float* out = reinterpret_cast<float*>(g.C) + c_row * g.ldc + col_off;
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(out + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+                for (int i = 0; i < 32 && n0 + i < g.N; ++i) out[i] = v[i];
+            }
+        } else {
+            bf16* out = reinterpret_cast<bf16*>(g.C) + c_row * g.ldc + col_off;
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 w;
+                    w.x = pack_bf16(v[i], v[i + 1]); w.y = pack_bf16(v[i + 2], v[i + 3]);
+                    w.z = pack_bf16(v[i + 4], v[i + 5]); w.w = pack_bf16(v[i + 6], v[i + 7]);
+                    *reinterpret_cast<uint4*>(out + i) = w;
+                }
+            } else {
+                for (int i = 0; i < 32 && n0 + i < g.N; ++i) out[i] = __float2bfloat16(v[i]);
+            }
+        }
+    }
+    }
+}
+
+template <int BLOCK_N, int STAGES, int INFLIGHT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
@@ -130,87 +231,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             const float* add_row = g.add ? g.add + (m_flat % g.add_rows) * g.ld_add : nullptr;
             mbar_wait(&tmem_full[a], aph);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = half; c < BLOCK_N / 32; c += 2) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + a * BLOCK_N + c * 32, r);
-                tmem_ld_wait();
-                const int n0 = n_blk * BLOCK_N + c * 32;
-                if (n0 >= g.N) continue;                    // warp uniform
-                float v[32];
-                const bool full = g.vec_ok && n0 + 32 <= g.N;
-                // one coalesced bias load per chunk (lane i holds column n0 + i), broadcast by shuffle: written as 32 scalar
-                // loads ptxas serialised them through two registers and the epilogue, not the MMA, set the tile time
-                const float bv = (g.bias && n0 + lane < g.N) ? __ldg(g.bias + n0 + lane) : 0.f;
-                float4 q[8];
-                if (add_row && full && row_ok) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) q[i] = *reinterpret_cast<const float4*>(add_row + n0 + 4 * i);
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float x = __uint_as_float(r[i]);
-                    if (g.bias) x += __shfl_sync(0xffffffffu, bv, i);
-                    if (g.gelu) x = gelu_erf(x);
-                    v[i] = x;
-                }
-                if (!row_ok) continue;                      // rows past the batch: nothing to add or store (after the shuffles)
-                if (add_row) {
-                    if (full) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { v[4 * i] += q[i].x; v[4 * i + 1] += q[i].y; v[4 * i + 2] += q[i].z; v[4 * i + 3] += q[i].w; }
-                    } else {
-                        for (int i = 0; i < 32 && n0 + i < g.N; ++i) v[i] += add_row[n0 + i];
-                    }
-                }
-                if (g.C2) {                                  // fragment-major copy of cross K / V^T (see gemm.cuh)
-                    const int grp = n0 >> 6, c0 = n0 & 63, j = t;
-                    bf16* base = g.C2 + (long)b * g.c2_batch_stride + (long)grp * 64 * g.c2_keys;
-                    if (((grp / g.c2_heads) & 1) == 0) {
-                        bf16* dst = base + ((((j >> 4) * 2 + (c0 >> 5)) * 2 + ((j & 15) >> 3)) * 256) + (j & 7) * 32;
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            uint4 q;
-                            q.x = pack_bf16(v[i], v[i + 1]); q.y = pack_bf16(v[i + 2], v[i + 3]);
-                            q.z = pack_bf16(v[i + 4], v[i + 5]); q.w = pack_bf16(v[i + 6], v[i + 7]);
-                            *reinterpret_cast<uint4*>(dst + i) = q;
-                        }
-                    } else {
-                        const int n_kc = g.c2_keys >> 5;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int c = c0 + i;
-                            base[((((c >> 4) * n_kc + (j >> 5)) * 2 + ((c & 15) >> 3)) * 256) + ((c & 7) * 4 + ((j & 31) >> 3)) * 8 + (j & 7)] =
-                                __float2bfloat16(v[i]);
-                        }
-                    }
-                }
-                // split mode: 64-column groups (heads) are c_split_stride elements apart
-                const long col_off = g.c_split ? (long)(n0 >> 6) * g.c_split_stride + (n0 & 63) : (long)n0;
-                if (g.c_fp32) {
-                    float* out = reinterpret_cast<float*>(g.C) + c_row * g.ldc + col_off;
-                    if (full) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            *reinterpret_cast<float4*>(out + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    } else {
-                        for (int i = 0; i < 32 && n0 + i < g.N; ++i) out[i] = v[i];
-                    }
-                } else {
-                    bf16* out = reinterpret_cast<bf16*>(g.C) + c_row * g.ldc + col_off;
-                    if (full) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            uint4 q;
-                            q.x = pack_bf16(v[i], v[i + 1]); q.y = pack_bf16(v[i + 2], v[i + 3]);
-                            q.z = pack_bf16(v[i + 4], v[i + 5]); q.w = pack_bf16(v[i + 6], v[i + 7]);
-                            *reinterpret_cast<uint4*>(out + i) = q;
-                        }
-                    } else {
-                        for (int i = 0; i < 32 && n0 + i < g.N; ++i) out[i] = __float2bfloat16(v[i]);
-                    }
-                }
-            }
+            epilogue_tile<BLOCK_N, INFLIGHT>(g, tmem_base + ((uint32_t)(quad * 32) << 16) + a * BLOCK_N, half, lane, n_blk, b, t, row_ok, c_row, add_row);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[a]);
@@ -221,6 +242,126 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.  Each CTA stages 128 rows
+// of A and 128 of the tile's 256 B rows per k-block (32 KB instead of the 48 KB of the 128 x 256 single-CTA tile, so the
+// ring is PAIR_STAGES deep), the leader's MMA thread issues tcgen05.mma.cta_group::2 with M = 256, and each CTA's TMEM ends
+// up with its own 128 accumulator rows x 256 columns.  Per SM and per MMA the shared-memory traffic (operand reads + TMA
+// writes) drops from 192 to 128 bytes per clock - the single-CTA kernel sat on that port limit at ~65 % of the tensor rate.
+//
+//   full[s]       leader only, 1 arrival + 64 KB of transactions: both CTAs' TMA loads count on the leader's barrier
+//   empty[s]      both CTAs, signalled by the leader's multicast tcgen05.commit
+//   tmem_full[a]  both CTAs, multicast commit; tmem_empty[a] leader only, 16 arrivals (8 epilogue warps of each CTA)
+// ---------------------------------------------------------------------------------------------------------------------
+static constexpr int PAIR_N = 256, PAIR_STAGES = 6;
+
+template <int INFLIGHT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                         const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
+                         const GemmKernelArgs g) {
+    constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;            // 128 rows of A
+    constexpr uint32_t B_BYTES = (PAIR_N / 2) * BLOCK_K * 2;       // this CTA's half of the tile's B rows
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * PAIR_N;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PAIR_STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + PAIR_STAGES;
+    uint64_t* tmem_full = empty_bar + PAIR_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int num_tiles = g.num_m_tiles * g.num_n_tiles;           // m tiles are 256 rows here
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapA0);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < PAIR_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 16); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                            // the peer's barriers exist before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (threadIdx.x == 0) {
+        // ------------------------------ TMA producer (both CTAs) ------------------------------
+        int s = 0; uint32_t ph = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            const int n_blk = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
+            const int b = m_tile / g.m_tiles_per_batch, t0 = (m_tile % g.m_tiles_per_batch) * 256 + (int)rank * BLOCK_M;
+            for (int kb = 0; kb < g.num_kb; ++kb) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+                const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[s]), 0);
+                uint8_t* sa = smem + s * STAGE_BYTES;
+                const int mi = kb / g.kblocks_per_map, c0 = (kb % g.kblocks_per_map) * BLOCK_K;
+                const CUtensorMap* am = mi == 0 ? &mapA0 : (mi == 1 ? &mapA1 : &mapA2);
+                tma_load_3d_pair(sa, am, lead_full, c0, t0, b);
+                tma_load_2d_pair(sa + A_BYTES, &mapB, lead_full, kb * BLOCK_K, n_blk * PAIR_N + (int)rank * (PAIR_N / 2));
+                if (++s == PAIR_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (threadIdx.x == 32 && rank == 0) {
+        // ------------------------------ MMA issuer (leader CTA) ------------------------------
+        constexpr uint32_t idesc = umma_idesc_bf16(256, PAIR_N);
+        int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            mbar_wait(&tmem_empty[a], aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + a * PAIR_N;
+            for (int kb = 0; kb < g.num_kb; ++kb) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t da = umma_desc_k128(sa), db = umma_desc_k128(sa + A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / 16; ++k)
+                    umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                umma_commit_pair(&empty_bar[s], 3);
+                if (++s == PAIR_STAGES) { s = 0; ph ^= 1; }
+            }
+            umma_commit_pair(&tmem_full[a], 3);
+            if (++a == 2) { a = 0; aph ^= 1; }
+        }
+    } else if (warp >= 2) {
+        // ------------------------------ epilogue (both CTAs: own 128 rows x 256 columns) ------------------------------
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        int a = 0; uint32_t aph = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            const int n_blk = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
+            const int b = m_tile / g.m_tiles_per_batch, t0 = (m_tile % g.m_tiles_per_batch) * 256 + (int)rank * BLOCK_M;
+            const int t = t0 + quad * 32 + lane;
+            const bool row_ok = t < g.rows_per_batch;
+            const long c_row = (long)b * g.c_batch_rows + g.c_row0 + t;
+            const long m_flat = (long)b * g.rows_per_batch + t;
+            const float* add_row = g.add ? g.add + (m_flat % g.add_rows) * g.ld_add : nullptr;
+            mbar_wait(&tmem_full[a], aph);
+            tc_fence_after();
+            epilogue_tile<PAIR_N, INFLIGHT>(g, tmem_base + ((uint32_t)(quad * 32) << 16) + a * PAIR_N, half, lane, n_blk, b, t, row_ok, c_row, add_row);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[a]), 0));
+            if (++a == 2) { a = 0; aph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                            // both CTAs are done with both TMEMs and shared memories
+    if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tmem_base, TMEM_COLS); }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -282,8 +423,11 @@ void gemm_clear_map_cache() { g_map_cache.clear(); }
 
 static int g_num_sms = 0;
 
-template <int BLOCK_N, int STAGES>
+// BLOCK_N == 0 selects the CTA-pair kernel (256 x 256 tiles)
+template <int BLOCK_N, int STAGES, int INFLIGHT>
 static void launch(const GemmParams& p, cudaStream_t stream) {
+    constexpr bool PAIR = BLOCK_N == 0;
+    constexpr int TILE_M = PAIR ? 256 : BLOCK_M, TILE_N = PAIR ? PAIR_N : BLOCK_N, B_BOX = PAIR ? PAIR_N / 2 : BLOCK_N;
     const CUtensorMap* am[3] = {nullptr, nullptr, nullptr};
     for (int i = 0; i < p.num_a_maps; ++i) {
         uint64_t dims[3] = {(uint64_t)p.a_inner, (uint64_t)p.rows_per_batch, (uint64_t)p.batch};
@@ -294,13 +438,13 @@ static void launch(const GemmParams& p, cudaStream_t stream) {
     for (int i = p.num_a_maps; i < 3; ++i) am[i] = am[0];
     uint64_t bdims[2] = {(uint64_t)p.K, (uint64_t)p.N};
     uint64_t bstr[1] = {(uint64_t)p.ldb * 2};
-    const CUtensorMap* bm = cached_map(p.B, 2, bdims, bstr, BLOCK_N);
+    const CUtensorMap* bm = cached_map(p.B, 2, bdims, bstr, B_BOX);
     if (!bm) return;
 
     GemmKernelArgs g;
     g.num_a_maps = p.num_a_maps; g.kblocks_per_map = p.kblocks_per_map; g.num_kb = p.K / BLOCK_K;
-    g.rows_per_batch = p.rows_per_batch; g.m_tiles_per_batch = cdiv(p.rows_per_batch, BLOCK_M);
-    g.num_m_tiles = g.m_tiles_per_batch * p.batch; g.num_n_tiles = cdiv(p.N, BLOCK_N);
+    g.rows_per_batch = p.rows_per_batch; g.m_tiles_per_batch = cdiv(p.rows_per_batch, TILE_M);
+    g.num_m_tiles = g.m_tiles_per_batch * p.batch; g.num_n_tiles = cdiv(p.N, TILE_N);
     g.N = p.N; g.bias = p.bias; g.gelu = p.gelu; g.add = p.add; g.add_rows = p.add_rows > 0 ? p.add_rows : 1;
     g.ld_add = p.ld_add; g.C = p.C; g.c_fp32 = p.c_fp32; g.ldc = p.ldc; g.c_batch_rows = p.c_batch_rows; g.c_row0 = p.c_row0;
     g.c_split = p.c_split; g.c_split_stride = p.c_split_stride;
@@ -309,30 +453,48 @@ static void launch(const GemmParams& p, cudaStream_t stream) {
     g.vec_ok = ((p.ldc * c_elem) % 16 == 0) && (((uintptr_t)p.C) % 16 == 0) && ((p.c_split_stride * c_elem) % 16 == 0) &&
                (!p.add || (((p.ld_add * 4) % 16 == 0) && (((uintptr_t)p.add) % 16 == 0)));
 
-    constexpr size_t smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    { static int skip = -1; if (skip < 0) { const char* e = getenv("B200_GEMM_SKIP"); skip = e ? atoi(e) : 0; } g.dbg_skip = skip; }
     if (!g_num_sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int tiles = g.num_m_tiles * g.num_n_tiles;
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_tcgen05_kernel<BLOCK_N, STAGES><<<grid, GEMM_THREADS, smem, stream>>>(*am[0], *am[1], *am[2], *bm, g);
+    static bool attr_set = false;
+    if constexpr (PAIR) {
+        constexpr size_t smem = PAIR_STAGES * (BLOCK_M * BLOCK_K * 2 + (PAIR_N / 2) * BLOCK_K * 2) + 1024 + 256;
+        if (!attr_set) {
+            B200_CHECK(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<INFLIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
+        gemm_tcgen05_pair_kernel<INFLIGHT><<<2 * pairs, GEMM_THREADS, smem, stream>>>(*am[0], *am[1], *am[2], *bm, g);
+    } else {
+        constexpr size_t smem = STAGES * (BLOCK_M * BLOCK_K * 2 + TILE_N * BLOCK_K * 2) + 1024 + 256;
+        if (!attr_set) {
+            B200_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<TILE_N, STAGES, INFLIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+        gemm_tcgen05_kernel<TILE_N, STAGES, INFLIGHT><<<grid, GEMM_THREADS, smem, stream>>>(*am[0], *am[1], *am[2], *bm, g);
+    }
     B200_LAUNCH_CHECK();
 }
 
+int g_gemm_force = -1;       // tests: 0 = automatic, 1 = 128x128, 2 = 128x256, 3 = CTA pair 256x256
+
 void gemm_tcgen05(const GemmParams& p, cudaStream_t stream) {
     if (p.K % BLOCK_K != 0) { record_error("gemm_tcgen05: K=%d is not a multiple of 64", p.K); return; }
-    // 128x256 tiles keep the smem operand read rate under the 128 B/clk port limit; fall back to
-    // 128x128 when the problem would not give every SM a tile.
+    if (g_gemm_force < 0) { const char* e = getenv("B200_GEMM_TILE"); g_gemm_force = e ? atoi(e) : 0; }
+    // CTA pairs (256x256) when that gives most pairs a tile; 128x256 single-CTA tiles keep the smem operand read rate under
+    // the 128 B/clk port limit; 128x128 when the problem would not give every SM a tile.
     const long tiles256 = (long)p.batch * cdiv(p.rows_per_batch, BLOCK_M) * cdiv(p.N, 256);
-    if (tiles256 >= 120 && p.N >= 256) launch<256, 4>(p, stream);
-    else launch<128, 6>(p, stream);
+    const long tiles_pair = (long)p.batch * cdiv(p.rows_per_batch, 256) * cdiv(p.N, 256);
+    int sel = g_gemm_force;
+    if (sel == 0) sel = (tiles_pair >= 60 && p.N >= 256) ? 3 : (tiles256 >= 120 && p.N >= 256) ? 2 : 1;
+    if (sel == 3) launch<0, PAIR_STAGES, 1>(p, stream);
+    else if (sel == 2) launch<256, 4, 1>(p, stream);
+    else launch<128, 6, 1>(p, stream);
 }
 
 GemmParams gemm_plain(const bf16* A, const bf16* B, void* C, int M, int N, int K) {
