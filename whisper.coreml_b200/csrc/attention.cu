@@ -3,7 +3,7 @@
 // [token][3d] QKV activation through 4-D TMA maps (dim, token, head, window).
 //
 //   CTA  = 128 queries of one (head, window); 2 CTAs per SM so one CTA's softmax overlaps the other's MMAs
-//   warp 0 : TMA producer   Q once, then K_j / V_j (64 keys) through a 4-stage ring
+//   warp 0 : TMA producer   Q once, then K_j / V_j (64 keys) through a 3-stage ring
 //   warp 1 : MMA issuer     S_j = Q K_j^T   -> TMEM S[j & 1]   (128 x 64 fp32)
 //                           O_j = P_j V_j   -> TMEM Oblk       (128 x 64 fp32, fresh each block)
 //   warps 2-5 : softmax     one query row per thread: tcgen05.ld S -> online max/sum in the log2 domain ->
@@ -19,9 +19,9 @@
 
 namespace b200 {
 
-constexpr int FA_BM = 128, FA_BN = 64, FA_STAGES = 4, FA_THREADS = 192;
+constexpr int FA_BM = 128, FA_BN = 64, FA_STAGES = 3, FA_THREADS = 192;      // 3 stages: 97 KB per CTA, two CTAs fit one SM
 constexpr uint32_t FA_Q_BYTES = FA_BM * 64 * 2, FA_KV_BYTES = FA_BN * 64 * 2, FA_P_BYTES = FA_BM * FA_BN * 2;
-constexpr uint32_t FA_SMEM = FA_Q_BYTES + FA_STAGES * 2 * FA_KV_BYTES + 2 * FA_P_BYTES;     // 16 + 64 + 32 KB
+constexpr uint32_t FA_SMEM = FA_Q_BYTES + FA_STAGES * 2 * FA_KV_BYTES + 2 * FA_P_BYTES;     // 16 + 48 + 32 KB
 constexpr uint32_t FA_TMEM_COLS = 256;                     // S0 [0,64) S1 [64,128) Oblk [128,192)
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -29,6 +29,9 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+__device__ __forceinline__ float ex2_approx(float x) { float d; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(x)); return d; }
 
 struct FaArgs {
     int n_q, n_k, n_kb;
@@ -126,7 +129,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         float o[64];
 #pragma unroll
         for (int c = 0; c < 64; ++c) o[c] = 0.f;
-        float m = -INFINITY, l = 0.f;
+        // m: running row maximum of the raw scores; l: running sum of 2^((s - m) log2 e).  o holds the output relative to the
+        // maximum of the block BEFORE the newest folded one, so that folding a block is one FFMA per element:
+        // o <- o * alpha_prev + Oblk.
+        float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
         uint8_t* prow = sP + row * 128;
         for (int j = 0; j < a.n_kb; ++j) {
             const int sb = j & 1;
@@ -140,17 +146,19 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[sb]);
             const int nvalid = a.n_k - j * FA_BN;                  // keys past n_k were zero-filled by TMA
+            if (nvalid < FA_BN) {                                  // last block only (uniform)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (i >= nvalid) r0[i] = 0xff800000u;          // -inf
+                    if (i + 32 >= nvalid) r1[i] = 0xff800000u;
+                }
+            }
             float mx = m;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float v0 = __uint_as_float(r0[i]) * LOG2E, v1 = __uint_as_float(r1[i]) * LOG2E;
-                if (i >= nvalid) v0 = -INFINITY;
-                if (i + 32 >= nvalid) v1 = -INFINITY;
-                r0[i] = __float_as_uint(v0); r1[i] = __float_as_uint(v1);
-                mx = fmaxf(mx, fmaxf(v0, v1));
-            }
-            const float alpha = exp2f(m - mx);                     // 0 on the first block (m = -inf)
+            for (int i = 0; i < 32; ++i) mx = fmax3(mx, __uint_as_float(r0[i]), __uint_as_float(r1[i]));
+            const float alpha = ex2_approx((m - mx) * LOG2E);      // 0 on the first block (m = -inf)
             m = mx;
+            const float m2 = mx * LOG2E;
             float sum = 0.f;
             mbar_wait(&p_empty[sb], ((j >> 1) & 1) ^ 1);           // PV_{j-2} no longer reads this P buffer
             uint8_t* pb = prow + sb * FA_P_BYTES;
@@ -160,8 +168,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int i = c * 8 + e;
-                    const float v = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
-                    p[e] = exp2f(v - m);
+                    p[e] = ex2_approx(fmaf(__uint_as_float(i < 32 ? r0[i] : r1[i - 32]), LOG2E, -m2));
                     sum += p[e];
                 }
                 uint4 u;
@@ -172,7 +179,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             fence_proxy_async();                                   // generic-proxy smem writes -> visible to the UMMA (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[sb]);
-            if (j > 0) {                                           // fold in Oblk_{j-1} (relative to the previous max), then rescale
+            if (j > 0) {                                           // fold in Oblk_{j-1}
                 mbar_wait(o_full, (j - 1) & 1);
                 tc_fence_after();
                 tmem_ld_32x32(lane_addr + 2 * FA_BN, r0);
@@ -183,10 +190,11 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
                 if (lane == 0) mbar_arrive(o_empty);
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    o[c] = (o[c] + __uint_as_float(r0[c])) * alpha;
-                    o[c + 32] = (o[c + 32] + __uint_as_float(r1[c])) * alpha;
+                    o[c] = fmaf(o[c], alpha_prev, __uint_as_float(r0[c]));
+                    o[c + 32] = fmaf(o[c + 32], alpha_prev, __uint_as_float(r1[c]));
                 }
             }
+            alpha_prev = alpha;
         }
         {
             uint32_t r0[32], r1[32];
@@ -199,19 +207,16 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             if (q0 + row < a.n_q) {
                 bf16* op = a.O + (long)b * a.o_batch_stride + (long)h * a.o_head_stride + (long)(q0 + row) * a.ldo;
 #pragma unroll
-                for (int c = 0; c < 32; c += 8) {
+                for (int c = 0; c < 32; ++c) {
+                    o[c] = fmaf(o[c], alpha_prev, __uint_as_float(r0[c])) * inv;
+                    o[c + 32] = fmaf(o[c + 32], alpha_prev, __uint_as_float(r1[c])) * inv;
+                }
+#pragma unroll
+                for (int c = 0; c < 64; c += 8) {
                     uint4 u;
-                    u.x = pack_bf16((o[c] + __uint_as_float(r0[c])) * inv, (o[c + 1] + __uint_as_float(r0[c + 1])) * inv);
-                    u.y = pack_bf16((o[c + 2] + __uint_as_float(r0[c + 2])) * inv, (o[c + 3] + __uint_as_float(r0[c + 3])) * inv);
-                    u.z = pack_bf16((o[c + 4] + __uint_as_float(r0[c + 4])) * inv, (o[c + 5] + __uint_as_float(r0[c + 5])) * inv);
-                    u.w = pack_bf16((o[c + 6] + __uint_as_float(r0[c + 6])) * inv, (o[c + 7] + __uint_as_float(r0[c + 7])) * inv);
+                    u.x = pack_bf16(o[c], o[c + 1]); u.y = pack_bf16(o[c + 2], o[c + 3]);
+                    u.z = pack_bf16(o[c + 4], o[c + 5]); u.w = pack_bf16(o[c + 6], o[c + 7]);
                     *reinterpret_cast<uint4*>(op + c) = u;
-                    uint4 w;
-                    w.x = pack_bf16((o[c + 32] + __uint_as_float(r1[c])) * inv, (o[c + 33] + __uint_as_float(r1[c + 1])) * inv);
-                    w.y = pack_bf16((o[c + 34] + __uint_as_float(r1[c + 2])) * inv, (o[c + 35] + __uint_as_float(r1[c + 3])) * inv);
-                    w.z = pack_bf16((o[c + 36] + __uint_as_float(r1[c + 4])) * inv, (o[c + 37] + __uint_as_float(r1[c + 5])) * inv);
-                    w.w = pack_bf16((o[c + 38] + __uint_as_float(r1[c + 6])) * inv, (o[c + 39] + __uint_as_float(r1[c + 7])) * inv);
-                    *reinterpret_cast<uint4*>(op + 32 + c) = w;
                 }
             }
         }
