@@ -175,6 +175,8 @@ void b200TestGetKV(float* out, int n_rows);
 /* softmax(Q K^T) V per head over a fused DEVICE [batch][n_tok][3*heads*64] bf16 QKV buffer ->
  * [batch][n_tok][heads*64] bf16: the tcgen05 flash-attention kernel, or the SIMT checker. */
 void b200TestAttention(const void* dQKV, void* dO, int n_tok, int heads, int batch, int use_simt);
+/* Average device time in ms of `iters` back-to-back launches of the tcgen05 flash-attention kernel. */
+float b200TestAttentionTime(const void* dQKV, void* dO, int n_tok, int heads, int batch, int iters);
 /* Stage timeline of the persistent decoder step kernel: enable=1 starts recording CTA 0's %globaltimer after every
  * grid barrier of the following steps; enable=0 copies up to `cap` timestamps (ns) to `out` and returns the count. */
 int b200TestStepTimeline(int enable, unsigned long long* out, int cap);

@@ -52,12 +52,17 @@ def test_gemm_cta_pair(lib, M, N, K, fp32, gelu, bias):
     assert _rel(C.float(), ref) < (1e-5 if fp32 else 4e-3)
 
 
+@pytest.mark.parametrize("ramp", [0.0, 6.0])
 @pytest.mark.parametrize("n_tok,heads,batch", [(1500, 6, 1), (1500, 20, 2), (128, 2, 1), (77, 1, 3), (200, 4, 1)])
-def test_flash_attention_tcgen05(lib, n_tok, heads, batch):
+def test_flash_attention_tcgen05(lib, n_tok, heads, batch, ramp):
+    """ramp > 0 makes the keys grow along the sequence, so the running row maximum keeps rising and the kernel's lazy
+    rescale of the TMEM-resident output fires in most key blocks."""
     d = heads * 64
     g = torch.Generator(device="cuda").manual_seed(n_tok + heads)
     qkv = torch.randn(batch, n_tok, 3 * d, device="cuda", generator=g)
     qkv[..., :d] *= 0.5                                   # scores with a few units of spread, like 0.125-scaled encoder keys
+    if ramp:
+        qkv[..., d:2 * d] *= (1.0 + ramp * torch.arange(n_tok, device="cuda") / n_tok)[None, :, None]
     qkv = qkv.bfloat16().contiguous()
     out = torch.full((batch, n_tok, d), float("nan"), device="cuda", dtype=torch.bfloat16)
     chk = torch.empty_like(out)

@@ -124,6 +124,30 @@ extern "C" void b200TestAttention(const void* dQKV, void* dO, int n_tok, int hea
     B200_CHECK(cudaStreamSynchronize(S().stream));
 }
 
+// average device time (ms) of `iters` back-to-back tcgen05 flash-attention launches over the same buffers
+extern "C" float b200TestAttentionTime(const void* dQKV, void* dO, int n_tok, int heads, int batch, int iters) {
+    use_device();
+    const long d = (long)heads * 64;
+    AttnParams a{};
+    a.Q = (const bf16*)dQKV; a.K = a.Q + d; a.V = a.Q + 2 * d;
+    a.ldq = a.ldk = a.ldv = 3 * d; a.q_head_stride = a.k_head_stride = a.v_head_stride = 64;
+    a.q_batch_stride = a.k_batch_stride = a.v_batch_stride = (long)n_tok * 3 * d;
+    a.O = (bf16*)dO; a.ldo = d; a.o_head_stride = 64; a.o_batch_stride = (long)n_tok * d;
+    a.n_q = a.n_k = n_tok; a.n_head = heads; a.batch = batch;
+    B200_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) attention_tc(a, S().stream);
+    cudaEventRecord(e0, S().stream);
+    for (int i = 0; i < iters; ++i) attention_tc(a, S().stream);
+    cudaEventRecord(e1, S().stream);
+    B200_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms / (iters > 0 ? iters : 1);
+}
+
 // Stage timeline of the persistent step kernel: enable = 1 allocates/clears the buffer (every following step overwrites
 // it: mark k of CTA c = %globaltimer ns at out[c * MEGA_DBG_LD + k]; mark 0 = start, 2i+1 / 2i+2 = after the prologue /
 // body of stage i); enable = 0 copies the last step's marks of up to `cap_ctas` CTAs to `out` and returns the CTA count.

@@ -6,9 +6,16 @@
 //   warp 0 : TMA producer   Q once, then K_j / V_j (64 keys) through a 3-stage ring
 //   warp 1 : MMA issuer     S_j = Q K_j^T   -> TMEM S[j & 1]   (128 x 64 fp32)
 //                           O_j = P_j V_j   -> TMEM Oblk       (128 x 64 fp32, fresh each block)
-//   warps 2-5 : softmax     one query row per thread: tcgen05.ld S -> online max/sum in the log2 domain ->
-//                           P_j (bf16) into 128B-swizzled smem as the A operand of the second MMA ->
-//                           o = (o + Oblk_{j-1}) * alpha_j in registers (no TMEM read-modify-write)
+//   warps 2-5 : softmax     one query row per thread: tcgen05.ld S -> running max / sum in the log2 domain ->
+//                           P_j (bf16 pairs) into TMEM with tcgen05.st: the A operand of the second MMA comes from TMEM, so
+//                           a block moves 48 KB through shared memory (Q, K, V reads + the TMA writes) instead of 80
+//
+// O accumulates in TMEM across the key blocks (PV_j with accumulate = 1), so the softmax warps never wait for a PV MMA: the
+// chain of a block is  S ready -> tcgen05.ld -> max -> exp2 -> P -> arrive.  The running maximum baked into O and l is only
+// raised when some row of the warp outgrows it by more than 2^8 (lazy rescale: P stays <= 256, exact in the end because O
+// and l share the factor); then the warp waits for PV_{j-1}, multiplies its 32 O rows in TMEM (tcgen05.ld / st) and goes on.
+// (An earlier version kept O in registers and folded every block's PV result: the wait -> ld -> fold chain through the MMA
+// warp, not the exp2, set the block time - with all arithmetic removed it still took 60 of 64 us.)
 //
 // V_j is consumed straight from its [key][dim] rows as an MN-major B operand.  Per (128 x 64) block the
 // tensor pipe needs 256 cycles and the 8192 exp2 need 512 MUFU cycles, so the kernel is exp-bound by design.
@@ -20,9 +27,10 @@
 namespace b200 {
 
 constexpr int FA_BM = 128, FA_BN = 64, FA_STAGES = 3, FA_THREADS = 192;      // 3 stages: 97 KB per CTA, two CTAs fit one SM
-constexpr uint32_t FA_Q_BYTES = FA_BM * 64 * 2, FA_KV_BYTES = FA_BN * 64 * 2, FA_P_BYTES = FA_BM * FA_BN * 2;
-constexpr uint32_t FA_SMEM = FA_Q_BYTES + FA_STAGES * 2 * FA_KV_BYTES + 2 * FA_P_BYTES;     // 16 + 48 + 32 KB
-constexpr uint32_t FA_TMEM_COLS = 256;                     // S0 [0,64) S1 [64,128) Oblk [128,192)
+constexpr uint32_t FA_Q_BYTES = FA_BM * 64 * 2, FA_KV_BYTES = FA_BN * 64 * 2;
+constexpr uint32_t FA_SMEM = FA_Q_BYTES + FA_STAGES * 2 * FA_KV_BYTES + 256;                // 16 + 48 KB + barriers
+constexpr uint32_t FA_TMEM_COLS = 256;                     // S0 [0,64) S1 [64,128) O [128,192) P0 [192,224) P1 [224,256) (bf16 pairs)
+constexpr uint32_t FA_P_COL = 192;
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -46,8 +54,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + FA_Q_BYTES;                                  // [stage][64 keys][64 dims]
     uint8_t* sV = sK + FA_STAGES * FA_KV_BYTES;
-    uint8_t* sP = sV + FA_STAGES * FA_KV_BYTES;                     // [2][128 rows][64 keys]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_P_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FA_STAGES * FA_KV_BYTES);
     uint64_t* q_full = bars;                 // 1
     uint64_t* kv_full = bars + 1;            // STAGES
     uint64_t* kv_empty = kv_full + FA_STAGES;
@@ -55,9 +62,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     uint64_t* s_empty = s_full + 2;          // 2
     uint64_t* p_full = s_empty + 2;          // 2
     uint64_t* p_empty = p_full + 2;          // 2
-    uint64_t* o_full = p_empty + 2;          // 1
-    uint64_t* o_empty = o_full + 1;          // 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+    uint64_t* pv_done = p_empty + 2;         // 1: completes once per PV_j
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
@@ -67,7 +73,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         mbar_init(q_full, 1);
         for (int s = 0; s < FA_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); mbar_init(&p_full[s], 4); mbar_init(&p_empty[s], 1); }
-        mbar_init(o_full, 1); mbar_init(o_empty, 4);
+        mbar_init(pv_done, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, FA_TMEM_COLS);
@@ -82,7 +88,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         tma_load_4d(sQ, &mapQ, q_full, 0, q0, h, b);
         int s = 0; uint32_t ph = 0;
         for (int j = 0; j < a.n_kb; ++j) {
-            mbar_wait(&kv_empty[s], ph ^ 1);
+            while (!mbar_try_wait(&kv_empty[s], ph ^ 1)) __nanosleep(128);   // the producer shares a scheduler with a softmax warp: do not spin
             mbar_expect_tx(&kv_full[s], 2 * FA_KV_BYTES);
             tma_load_4d(sK + s * FA_KV_BYTES, &mapK, &kv_full[s], 0, j * FA_BN, h, b);
             tma_load_4d(sV + s * FA_KV_BYTES, &mapV, &kv_full[s], 0, j * FA_BN, h, b);
@@ -109,14 +115,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             if (j + 1 < a.n_kb) issue_qk(j + 1);                   // keep the tensor pipe busy while softmax_j runs
             const int s = j % FA_STAGES, sb = j & 1;
             mbar_wait(&p_full[sb], (j >> 1) & 1);
-            mbar_wait(o_empty, (j & 1) ^ 1);
             tc_fence_after();
-            const uint64_t dp = umma_desc_k128(smem_u32(sP + sb * FA_P_BYTES));
             const uint64_t dv = umma_desc_mn128(smem_u32(sV + s * FA_KV_BYTES), 8192);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)                            // 16 keys per MMA: +32 B in P rows, +2 x 1024 B in V
-                umma_bf16(tmem + 2 * FA_BN, dp + 2 * k, dv + 128 * k, idesc_pv, k != 0);
-            umma_commit(o_full);
+            for (int k = 0; k < 4; ++k)                            // 16 keys per MMA: 8 TMEM columns of P (bf16 pairs), +2 x 1024 B in V
+                umma_bf16_ts(tmem + 2 * FA_BN, tmem + FA_P_COL + sb * 32 + k * 8, dv + 128 * k, idesc_pv, (j | k) != 0);
+            umma_commit(pv_done);
             umma_commit(&kv_empty[s]);
             umma_commit(&p_empty[sb]);
         }
@@ -126,14 +130,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         const int row = quad * 32 + lane;                          // TMEM lane == query row of the tile
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
         const float LOG2E = 1.4426950408889634f;
-        float o[64];
-#pragma unroll
-        for (int c = 0; c < 64; ++c) o[c] = 0.f;
-        // m: running row maximum of the raw scores; l: running sum of 2^((s - m) log2 e).  o holds the output relative to the
-        // maximum of the block BEFORE the newest folded one, so that folding a block is one FFMA per element:
-        // o <- o * alpha_prev + Oblk.
-        float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-        uint8_t* prow = sP + row * 128;
+        // m: the row maximum (raw scores) that O and l are currently relative to; l: running sum of 2^((s - m) log2 e)
+        float m = -INFINITY, l = 0.f;
         for (int j = 0; j < a.n_kb; ++j) {
             const int sb = j & 1;
             mbar_wait(&s_full[sb], (j >> 1) & 1);
@@ -153,52 +151,60 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
                     if (i + 32 >= nvalid) r1[i] = 0xff800000u;
                 }
             }
-            float mx = m;
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmax3(mx, __uint_as_float(r0[i]), __uint_as_float(r1[i]));
-            const float alpha = ex2_approx((m - mx) * LOG2E);      // 0 on the first block (m = -inf)
-            m = mx;
-            const float m2 = mx * LOG2E;
-            float sum = 0.f;
-            mbar_wait(&p_empty[sb], ((j >> 1) & 1) ^ 1);           // PV_{j-2} no longer reads this P buffer
-            uint8_t* pb = prow + sb * FA_P_BYTES;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {                          // 8 chunks of 8 keys (16 B), 128B swizzle: chunk ^= row & 7
-                float p[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int i = c * 8 + e;
-                    p[e] = ex2_approx(fmaf(__uint_as_float(i < 32 ? r0[i] : r1[i - 32]), LOG2E, -m2));
-                    sum += p[e];
-                }
-                uint4 u;
-                u.x = pack_bf16(p[0], p[1]); u.y = pack_bf16(p[2], p[3]); u.z = pack_bf16(p[4], p[5]); u.w = pack_bf16(p[6], p[7]);
-                *reinterpret_cast<uint4*>(pb + ((c ^ (row & 7)) << 4)) = u;
-            }
-            l = l * alpha + sum;
-            fence_proxy_async();                                   // generic-proxy smem writes -> visible to the UMMA (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[sb]);
-            if (j > 0) {                                           // fold in Oblk_{j-1}
-                mbar_wait(o_full, (j - 1) & 1);
+            for (int i = 0; i < 32; ++i) mx4[i & 3] = fmax3(mx4[i & 3], __uint_as_float(r0[i]), __uint_as_float(r1[i]));
+            const float mx = fmax3(fmaxf(mx4[0], mx4[1]), mx4[2], mx4[3]);
+            if (j == 0) {
+                m = mx;
+            } else if (__any_sync(0xffffffffu, (mx - m) * LOG2E > 8.f)) {
+                // lazy rescale (warp uniform): raise every row of the warp to its exact maximum
+                const float mnew = fmaxf(m, mx);
+                const float alpha = ex2_approx((m - mnew) * LOG2E);
+                m = mnew;
+                l *= alpha;
+                mbar_wait(pv_done, (j - 1) & 1);                   // PV_0 .. PV_{j-1} have landed in O
                 tc_fence_after();
-                tmem_ld_32x32(lane_addr + 2 * FA_BN, r0);
-                tmem_ld_32x32(lane_addr + 2 * FA_BN + 32, r1);
+                uint32_t q0r[32], q1r[32];
+                tmem_ld_32x32(lane_addr + 2 * FA_BN, q0r);
+                tmem_ld_32x32(lane_addr + 2 * FA_BN + 32, q1r);
                 tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(o_empty);
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    o[c] = fmaf(o[c], alpha_prev, __uint_as_float(r0[c]));
-                    o[c + 32] = fmaf(o[c + 32], alpha_prev, __uint_as_float(r1[c]));
+                    q0r[c] = __float_as_uint(__uint_as_float(q0r[c]) * alpha);
+                    q1r[c] = __float_as_uint(__uint_as_float(q1r[c]) * alpha);
                 }
+                tmem_st_32x32(lane_addr + 2 * FA_BN, q0r);
+                tmem_st_32x32(lane_addr + 2 * FA_BN + 32, q1r);
+                tmem_st_wait();
+                tc_fence_before();                                 // ordered before PV_j through the p_full arrive below
             }
-            alpha_prev = alpha;
+            const float m2 = m * LOG2E;
+            float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+            mbar_wait(&p_empty[sb], ((j >> 1) & 1) ^ 1);           // PV_{j-2} no longer reads this P buffer
+            uint32_t pk[32];                                       // P_j as bf16 pairs: the A operand of PV_j, read from TMEM
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float pa = ex2_approx(fmaf(__uint_as_float(r0[i]), LOG2E, -m2));
+                const float pb = ex2_approx(fmaf(__uint_as_float(r1[i]), LOG2E, -m2));
+                sum4[i & 3] += pa + pb;
+                r0[i] = __float_as_uint(pa); r1[i] = __float_as_uint(pb);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                pk[i] = pack_bf16(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
+                pk[16 + i] = pack_bf16(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1]));
+            }
+            tmem_st_32x32(lane_addr + FA_P_COL + sb * 32, pk);
+            tmem_st_wait();
+            l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[sb]);
         }
         {
             uint32_t r0[32], r1[32];
-            mbar_wait(o_full, (a.n_kb - 1) & 1);
+            mbar_wait(pv_done, (a.n_kb - 1) & 1);
             tc_fence_after();
             tmem_ld_32x32(lane_addr + 2 * FA_BN, r0);
             tmem_ld_32x32(lane_addr + 2 * FA_BN + 32, r1);
@@ -207,16 +213,18 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             if (q0 + row < a.n_q) {
                 bf16* op = a.O + (long)b * a.o_batch_stride + (long)h * a.o_head_stride + (long)(q0 + row) * a.ldo;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    o[c] = fmaf(o[c], alpha_prev, __uint_as_float(r0[c])) * inv;
-                    o[c + 32] = fmaf(o[c + 32], alpha_prev, __uint_as_float(r1[c])) * inv;
-                }
-#pragma unroll
-                for (int c = 0; c < 64; c += 8) {
-                    uint4 u;
-                    u.x = pack_bf16(o[c], o[c + 1]); u.y = pack_bf16(o[c + 2], o[c + 3]);
-                    u.z = pack_bf16(o[c + 4], o[c + 5]); u.w = pack_bf16(o[c + 6], o[c + 7]);
+                for (int c = 0; c < 32; c += 8) {
+                    uint4 u, w;
+                    u.x = pack_bf16(__uint_as_float(r0[c]) * inv, __uint_as_float(r0[c + 1]) * inv);
+                    u.y = pack_bf16(__uint_as_float(r0[c + 2]) * inv, __uint_as_float(r0[c + 3]) * inv);
+                    u.z = pack_bf16(__uint_as_float(r0[c + 4]) * inv, __uint_as_float(r0[c + 5]) * inv);
+                    u.w = pack_bf16(__uint_as_float(r0[c + 6]) * inv, __uint_as_float(r0[c + 7]) * inv);
+                    w.x = pack_bf16(__uint_as_float(r1[c]) * inv, __uint_as_float(r1[c + 1]) * inv);
+                    w.y = pack_bf16(__uint_as_float(r1[c + 2]) * inv, __uint_as_float(r1[c + 3]) * inv);
+                    w.z = pack_bf16(__uint_as_float(r1[c + 4]) * inv, __uint_as_float(r1[c + 5]) * inv);
+                    w.w = pack_bf16(__uint_as_float(r1[c + 6]) * inv, __uint_as_float(r1[c + 7]) * inv);
                     *reinterpret_cast<uint4*>(op + c) = u;
+                    *reinterpret_cast<uint4*>(op + 32 + c) = w;
                 }
             }
         }

@@ -60,26 +60,38 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& g, uint32_t 
     uint32_t r[NF][32];
 #pragma unroll
     for (int u = 0; u < NF; ++u) tmem_ld_32x32(tmem_acc + (half + 2 * (s0 + u)) * 32, r[u]);
+    // the bias and residual loads of the chunk are issued BEFORE the wait for the TMEM load: their L2 latency was on the
+    // epilogue's critical path four times per tile
+    float bvs[NF]; float4 qs[NF][8];
+#pragma unroll
+    for (int u = 0; u < NF; ++u) {
+        const int n0 = n_blk * BLOCK_N + (half + 2 * (s0 + u)) * 32;
+        bvs[u] = (g.bias && n0 + lane < g.N) ? __ldg(g.bias + n0 + lane) : 0.f;   // lane i holds column n0 + i; broadcast by shuffle below
+        if (add_row && row_ok && g.vec_ok && n0 + 32 <= g.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) qs[u][i] = *reinterpret_cast<const float4*>(add_row + n0 + 4 * i);
+        }
+    }
     tmem_ld_wait();
 #pragma unroll
     for (int u = 0; u < NF; ++u) {
         const int n0 = n_blk * BLOCK_N + (half + 2 * (s0 + u)) * 32;
         if (n0 >= g.N) continue;                        // warp uniform
         const bool full = g.vec_ok && n0 + 32 <= g.N;
-        float4 q[8];
-        if (add_row && full && row_ok) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) q[i] = *reinterpret_cast<const float4*>(add_row + n0 + 4 * i);
-        }
-        // one coalesced bias load per sub-chunk (lane i holds column n0 + i), broadcast by shuffle
-        const float bv = (g.bias && n0 + lane < g.N) ? __ldg(g.bias + n0 + lane) : 0.f;
+        const float bv = bvs[u];
+        float4 (&q)[8] = qs[u];
+        // the (kernel-uniform) epilogue kind is tested OUTSIDE the element loops: as per-element branches it kept ptxas from
+        // interleaving the 32 independent elements (46 instructions per element at 0.35 IPC in the MLP1 GEMM)
         float v[32];
+        if (g.gelu) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(r[u][i]);
-            if (g.bias) x += __shfl_sync(0xffffffffu, bv, i);
-            if (g.gelu) x = gelu_erf(x);
-            v[i] = x;
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(__uint_as_float(r[u][i]) + __shfl_sync(0xffffffffu, bv, i));
+        } else if (g.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[u][i]) + __shfl_sync(0xffffffffu, bv, i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[u][i]);
         }
         if (g.dbg_skip == 1) { float acc = 0.f; for (int i = 0; i < 32; ++i) acc += v[i]; if (acc == 1.2345e-30f) reinterpret_cast<float*>(g.C)[0] = acc; continue; }
         if (!row_ok) continue;                          // rows past the batch: nothing to add or store (after the shuffles)
