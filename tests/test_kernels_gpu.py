@@ -28,6 +28,22 @@ def test_gemm_tcgen05(lib, M, N, K, fp32, gelu, bias):
     assert _rel(C.float(), ref) < (1e-5 if fp32 else 4e-3)
 
 
+def test_gemm_gelu_epilogue_accuracy(lib):
+    """The GEMM epilogue's erf-GELU is a fitted form (common.cuh: gelu_erf_fit): within 1e-4 absolute of torch's exact GELU."""
+    M, N, K = 256, 512, 64
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.6).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.6).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    C = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+    lib.b200TestGemm(A.data_ptr(), B.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, 1, 1, 0)
+    pre = A.double() @ B.double().t() + b.double()
+    ref = torch.nn.functional.gelu(pre)
+    assert float(pre.abs().max()) > 8.0                   # the saturated tails are exercised too
+    assert float((C.double() - ref).abs().max()) < 1e-4
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (3000, 1280, 1280), (1500, 3840, 1280), (3000, 5120, 1280), (3000, 1280, 5120), (777, 392, 192)])
 @pytest.mark.parametrize("fp32,gelu,bias", [(1, 0, 0), (0, 1, 1)])
 def test_gemm_cta_pair(lib, M, N, K, fp32, gelu, bias):

@@ -51,7 +51,7 @@ struct GemmKernelArgs {
 // batch of loads compete with the next tile's operand reads for the shared-memory / L1 data path).
 template <int BLOCK_N, int INFLIGHT>
 __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& g, uint32_t tmem_acc, int half, int lane, int n_blk, int b, int t,
-                                              bool row_ok, long c_row, const float* add_row) {
+                                              bool row_ok, long c_row, const float* add_row, float4* stage) {
     if (g.dbg_skip == 2) return;
     constexpr int NSUB = BLOCK_N / 64;                  // 32-column sub-chunks of this warp
     constexpr int NF = INFLIGHT < NSUB ? INFLIGHT : NSUB;
@@ -61,13 +61,25 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& g, uint32_t 
 #pragma unroll
     for (int u = 0; u < NF; ++u) tmem_ld_32x32(tmem_acc + (half + 2 * (s0 + u)) * 32, r[u]);
     // the bias and residual loads of the chunk are issued BEFORE the wait for the TMEM load: their L2 latency was on the
-    // epilogue's critical path four times per tile
+    // epilogue's critical path four times per tile.  fp32 chunks that lie fully inside N take the coalesced path (`tp`): the
+    // 32 x 32 chunk is transposed through 4 KB of shared memory per warp so that a warp instruction reads (residual) and
+    // writes four whole 128-byte row segments instead of 16 bytes of each of 32 rows; there lane l handles columns
+    // 4 (l & 7) .. + 3 of the rows 4 i + (l >> 3).  (Measured: out-projection 24.7 -> 18.6 us; for bf16 outputs the extra
+    // shared-memory traffic slowed the main loop more than the stores gained - MLP1 59 -> 67 us - so they store directly.)
+    const int sub = lane >> 3, ch = lane & 7;
     float bvs[NF]; float4 qs[NF][8];
 #pragma unroll
     for (int u = 0; u < NF; ++u) {
         const int n0 = n_blk * BLOCK_N + (half + 2 * (s0 + u)) * 32;
         bvs[u] = (g.bias && n0 + lane < g.N) ? __ldg(g.bias + n0 + lane) : 0.f;   // lane i holds column n0 + i; broadcast by shuffle below
-        if (add_row && row_ok && g.vec_ok && n0 + 32 <= g.N) {
+        const bool tp = g.vec_ok && n0 + 32 <= g.N && !g.C2 && g.c_fp32;
+        if (add_row && tp) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float* ar = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(add_row), 4 * i + sub));
+                qs[u][i] = *reinterpret_cast<const float4*>(ar + n0 + 4 * ch);
+            }
+        } else if (add_row && row_ok && g.vec_ok && n0 + 32 <= g.N) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) qs[u][i] = *reinterpret_cast<const float4*>(add_row + n0 + 4 * i);
         }
@@ -83,7 +95,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& g, uint32_t 
         // the (kernel-uniform) epilogue kind is tested OUTSIDE the element loops: as per-element branches it kept ptxas from
         // interleaving the 32 independent elements (46 instructions per element at 0.35 IPC in the MLP1 GEMM)
         float v[32];
-        if (g.gelu) {
+        if (g.gelu == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fit(__uint_as_float(r[u][i]) + __shfl_sync(0xffffffffu, bv, i));
+        } else if (g.gelu) {                            // B200_GELU_EXACT=1: erff()
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_erf(__uint_as_float(r[u][i]) + __shfl_sync(0xffffffffu, bv, i));
         } else if (g.bias) {
@@ -94,6 +109,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& g, uint32_t 
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[u][i]);
         }
         if (g.dbg_skip == 1) { float acc = 0.f; for (int i = 0; i < 32; ++i) acc += v[i]; if (acc == 1.2345e-30f) reinterpret_cast<float*>(g.C)[0] = acc; continue; }
+        if (full && !g.C2 && g.c_fp32) {                // coalesced path (warp uniform)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) stage[lane * 8 + (i ^ (lane & 7))] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            __syncwarp();
+            const long col = (g.c_split ? (long)(n0 >> 6) * g.c_split_stride + (n0 & 63) : (long)n0) + 4 * ch;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = 4 * i + sub;
+                float4 x = stage[rr * 8 + (ch ^ (rr & 7))];
+                if (add_row) { x.x += q[i].x; x.y += q[i].y; x.z += q[i].z; x.w += q[i].w; }
+                if (t - lane + rr < g.rows_per_batch) {
+                    const long off = (c_row - lane + rr) * g.ldc + col;
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + off) = x;
+                }
+            }
+            __syncwarp();                               // the next chunk overwrites the staging buffer
+            continue;
+        }
         if (!row_ok) continue;                          // rows past the batch: nothing to add or store (after the shuffles)
         if (add_row) {
             if (full) {
@@ -232,6 +265,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         // ------------------------------ epilogue ------------------------------
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
         const int half = (warp - 2) >> 2;                   // the two warps of a quadrant take alternate 32-column chunks
+        float4* stage = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * 256;   // 4 KB transposition buffer
         int a = 0; uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int n_blk = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
@@ -243,7 +277,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             const float* add_row = g.add ? g.add + (m_flat % g.add_rows) * g.ld_add : nullptr;
             mbar_wait(&tmem_full[a], aph);
             tc_fence_after();
-            epilogue_tile<BLOCK_N, INFLIGHT>(g, tmem_base + ((uint32_t)(quad * 32) << 16) + a * BLOCK_N, half, lane, n_blk, b, t, row_ok, c_row, add_row);
+            epilogue_tile<BLOCK_N, INFLIGHT>(g, tmem_base + ((uint32_t)(quad * 32) << 16) + a * BLOCK_N, half, lane, n_blk, b, t, row_ok, c_row, add_row, stage);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[a]);
@@ -351,6 +385,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid
         // ------------------------------ epilogue (both CTAs: own 128 rows x 256 columns) ------------------------------
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
+        float4* stage = reinterpret_cast<float4*>(smem + PAIR_STAGES * STAGE_BYTES + 256) + (warp - 2) * 256;
         int a = 0; uint32_t aph = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs) {
             const int n_blk = tile % g.num_n_tiles, m_tile = tile / g.num_n_tiles;
@@ -362,7 +397,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid
             const float* add_row = g.add ? g.add + (m_flat % g.add_rows) * g.ld_add : nullptr;
             mbar_wait(&tmem_full[a], aph);
             tc_fence_after();
-            epilogue_tile<PAIR_N, INFLIGHT>(g, tmem_base + ((uint32_t)(quad * 32) << 16) + a * PAIR_N, half, lane, n_blk, b, t, row_ok, c_row, add_row);
+            epilogue_tile<PAIR_N, INFLIGHT>(g, tmem_base + ((uint32_t)(quad * 32) << 16) + a * PAIR_N, half, lane, n_blk, b, t, row_ok, c_row, add_row, stage);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[a]), 0));
@@ -465,6 +500,7 @@ static void launch(const GemmParams& p, cudaStream_t stream) {
     g.vec_ok = ((p.ldc * c_elem) % 16 == 0) && (((uintptr_t)p.C) % 16 == 0) && ((p.c_split_stride * c_elem) % 16 == 0) &&
                (!p.add || (((p.ld_add * 4) % 16 == 0) && (((uintptr_t)p.add) % 16 == 0)));
 
+    { static int ex = -1; if (ex < 0) { const char* e = getenv("B200_GELU_EXACT"); ex = e ? atoi(e) : 0; } if (g.gelu && ex) g.gelu = 2; }
     { static int skip = -1; if (skip < 0) { const char* e = getenv("B200_GEMM_SKIP"); skip = e ? atoi(e) : 0; } g.dbg_skip = skip; }
     if (!g_num_sms) {
         int dev = 0;
@@ -474,7 +510,7 @@ static void launch(const GemmParams& p, cudaStream_t stream) {
     const int tiles = g.num_m_tiles * g.num_n_tiles;
     static bool attr_set = false;
     if constexpr (PAIR) {
-        constexpr size_t smem = PAIR_STAGES * (BLOCK_M * BLOCK_K * 2 + (PAIR_N / 2) * BLOCK_K * 2) + 1024 + 256;
+        constexpr size_t smem = PAIR_STAGES * (BLOCK_M * BLOCK_K * 2 + (PAIR_N / 2) * BLOCK_K * 2) + 1024 + 256 + 8 * 4096;
         if (!attr_set) {
             B200_CHECK(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<INFLIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
@@ -482,7 +518,7 @@ static void launch(const GemmParams& p, cudaStream_t stream) {
         const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
         gemm_tcgen05_pair_kernel<INFLIGHT><<<2 * pairs, GEMM_THREADS, smem, stream>>>(*am[0], *am[1], *am[2], *bm, g);
     } else {
-        constexpr size_t smem = STAGES * (BLOCK_M * BLOCK_K * 2 + TILE_N * BLOCK_K * 2) + 1024 + 256;
+        constexpr size_t smem = STAGES * (BLOCK_M * BLOCK_K * 2 + TILE_N * BLOCK_K * 2) + 1024 + 256 + 8 * 4096;
         if (!attr_set) {
             B200_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<TILE_N, STAGES, INFLIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
