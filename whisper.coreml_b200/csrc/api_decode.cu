@@ -145,12 +145,13 @@ static void launch_sampling(int nb, int k, bool shared_logits) {
     SampleArgs sa{};
     sa.logits = s.slogits; sa.ld_logits = shared_logits ? 0 : s.V; sa.tokens = c.tokens; sa.st = c.st; sa.spec = c.spec; sa.nb = nb; sa.k = k;
     sa.cand_lp = c.cand_lp; sa.cand_tok = c.cand_tok; sa.part = c.part;
-    sample_partial(sa, s.stream);
     BeamUpdateArgs ba{};
     ba.part = c.part; ba.timestamp_begin = c.spec.timestamp_begin; ba.update = 1;
     ba.cand_lp = c.cand_lp; ba.cand_tok = c.cand_tok; ba.nb = nb; ba.k = k; ba.tokens = c.tokens; ba.table = s.table;
     ba.fin_tokens = c.fin_tokens; ba.st = c.st; ba.eot = c.spec.eot; ba.n_text_ctx = N_TEXT_CTX;
-    beam_update(ba, s.stream);
+    static const bool split = getenv("B200_SAMPLING_SPLIT") && atoi(getenv("B200_SAMPLING_SPLIT")) != 0;   // two launches (the earlier form)
+    if (split) { sample_partial(sa, s.stream); beam_update(ba, s.stream); }
+    else sample_and_update(sa, ba, s.stream);
 }
 
 }  // namespace b200

@@ -33,6 +33,8 @@
 // the same CUDA graph.
 #include "decoder_mega.cuh"
 
+#include <stdlib.h>
+
 #include "sampling_dev.cuh"
 
 namespace b200 {
@@ -945,7 +947,11 @@ bool mega_launch(const MegaArgs& a, int n_ctas, cudaStream_t s) {
     }
     MegaArgs args = a;
     void* params[] = {(void*)&args};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)decoder_mega_kernel, dim3(n_ctas), dim3(MG_THREADS), params, smem, s);
+    // experiment (B200_MEGA_NOCOOP=1): a plain launch - every CTA needs a whole SM, so the grid is co-resident whenever
+    // the lanes' grids add up to at most the SM count, which api_decode.cu guarantees
+    static const bool nocoop = getenv("B200_MEGA_NOCOOP") && atoi(getenv("B200_MEGA_NOCOOP")) != 0;
+    cudaError_t e = nocoop ? cudaLaunchKernel((const void*)decoder_mega_kernel, dim3(n_ctas), dim3(MG_THREADS), params, smem, s)
+                           : cudaLaunchCooperativeKernel((const void*)decoder_mega_kernel, dim3(n_ctas), dim3(MG_THREADS), params, smem, s);
     ++g_launch_count;
     if (e != cudaSuccess) { cudaGetLastError(); record_error("decoder_mega launch: %s", cudaGetErrorString(e)); return false; }
     return true;

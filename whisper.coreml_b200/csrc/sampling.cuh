@@ -35,6 +35,7 @@ struct SamplePartials {                // device scratch
     float m[DEC_MAX_BEAMS][SAMPLE_CHUNKS], s[DEC_MAX_BEAMS][SAMPLE_CHUNKS];
     float topv[DEC_MAX_BEAMS][SAMPLE_CHUNKS][SAMPLE_MAX_K];
     int topi[DEC_MAX_BEAMS][SAMPLE_CHUNKS][SAMPLE_MAX_K];
+    unsigned arrivals;                 // CTAs of the fused kernel that have written their partial (re-armed by the last one)
 };
 struct SampleArgs {
     const float* logits; long ld_logits;   // [nb][V]
@@ -59,6 +60,8 @@ struct BeamUpdateArgs {
     int eot, n_text_ctx;
 };
 void beam_update(const BeamUpdateArgs& a, cudaStream_t s);
+// Both phases in ONE launch: the CTA whose partial arrives last runs phase 2 (one kernel boundary less per token step).
+void sample_and_update(const SampleArgs& a, const BeamUpdateArgs& u, cudaStream_t s);
 
 // st->no_speech_prob = softmax(logits)[no_speech]   (whisper/decoding.py:716-720)
 void no_speech_prob(const float* logits, int n_vocab, int no_speech, DecodeState* st, cudaStream_t s);
