@@ -37,7 +37,7 @@ def test_no_triton_or_torch_compile_in_product():
 def test_header_symbols_are_exported():
     hdr = open(os.path.join(ROOT, "include", "whisper_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(?:void|int|long)\s+([A-Za-z_][A-Za-z0-9_]*)\s*\(", hdr))
+    declared = set(re.findall(r"\b(?:void|int|long|float)\s+([A-Za-z_][A-Za-z0-9_]*)\s*\(", hdr))
     assert {"loadEncoder", "encoderPredict", "crossKVPredict", "decoder256Predict", "decoder1Predict", "rearrange_mkv"} <= declared
     from whisper_b200 import _lib
     lib = _lib.load()                          # loading needs no GPU
