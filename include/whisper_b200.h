@@ -177,6 +177,9 @@ void b200TestGetKV(float* out, int n_rows);
 void b200TestAttention(const void* dQKV, void* dO, int n_tok, int heads, int batch, int use_simt);
 /* Average device time in ms of `iters` back-to-back launches of the tcgen05 flash-attention kernel. */
 float b200TestAttentionTime(const void* dQKV, void* dO, int n_tok, int heads, int batch, int iters);
+/* clock64 marks of CTA (0,0,0) of one flash-attention launch, out[block * 16 + k]: k = 0-4 softmax warp (enter, S ready,
+ * S loaded, P buffer free, P published), 5-7 MMA thread (loop top, next QK issued, P seen); returns the key-block count. */
+int b200TestAttentionTimeline(const void* dQKV, void* dO, int n_tok, int heads, int batch, unsigned long long* out, int cap_blocks);
 /* Stage timeline of the persistent decoder step kernel: enable=1 starts recording CTA 0's %globaltimer after every
  * grid barrier of the following steps; enable=0 copies up to `cap` timestamps (ns) to `out` and returns the count. */
 int b200TestStepTimeline(int enable, unsigned long long* out, int cap);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "b200TestGetCrossKV": (None, [f32p, f32p, c_int]),
     "b200TestGetKV": (None, [f32p, c_int]),
     "b200TestAttention": (None, [c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
+    "b200TestAttentionTimeline": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int]),
     "b200TestAttentionTime": (ctypes.c_float, [c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
     "b200TestStepTimeline": (c_int, [c_int, c_void_p, c_int]),
 }

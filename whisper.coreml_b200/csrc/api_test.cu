@@ -148,6 +148,23 @@ extern "C" float b200TestAttentionTime(const void* dQKV, void* dO, int n_tok, in
     return ms / (iters > 0 ? iters : 1);
 }
 
+// clock64 marks of CTA (0,0,0) of one flash-attention launch: out[block * 16 + k], k = 0-4 softmax warp (enter, S ready, S loaded,
+// P buffer free, P published), 5-7 MMA thread (loop top, next QK issued, P seen); returns the number of key blocks
+namespace b200 { extern unsigned long long* g_fa_dbg; }
+extern "C" int b200TestAttentionTimeline(const void* dQKV, void* dO, int n_tok, int heads, int batch, unsigned long long* out, int cap_blocks) {
+    use_device();
+    const int n_kb = (n_tok + 63) / 64;
+    unsigned long long* d = nullptr;
+    if (!dev_alloc(&d, (size_t)n_kb * 16, true)) return 0;
+    g_fa_dbg = d;
+    b200TestAttention(dQKV, dO, n_tok, heads, batch, 0);
+    g_fa_dbg = nullptr;
+    const int n = n_kb < cap_blocks ? n_kb : cap_blocks;
+    B200_CHECK(cudaMemcpy(out, d, (size_t)n * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    dev_free(&d);
+    return n;
+}
+
 // Stage timeline of the persistent step kernel: enable = 1 allocates/clears the buffer (every following step overwrites
 // it: mark k of CTA c = %globaltimer ns at out[c * MEGA_DBG_LD + k]; mark 0 = start, 2i+1 / 2i+2 = after the prologue /
 // body of stage i); enable = 0 copies the last step's marks of up to `cap_ctas` CTAs to `out` and returns the CTA count.

@@ -3,9 +3,9 @@
 // [token][3d] QKV activation through 4-D TMA maps (dim, token, head, window).
 //
 //   CTA  = 128 queries of one (head, window); 2 CTAs per SM so one CTA's softmax overlaps the other's MMAs
-//   warp 0 : TMA producer   Q once, then K_j / V_j (64 keys) through a 3-stage ring
+//   warp 0 : TMA producer   Q once, then K_j / V_j (64 keys) through a 5-stage ring
 //   warp 1 : MMA issuer     S_j = Q K_j^T   -> TMEM S[j & 1]   (128 x 64 fp32)
-//                           O_j = P_j V_j   -> TMEM Oblk       (128 x 64 fp32, fresh each block)
+//                           O  += P_j V_j   -> TMEM O          (128 x 64 fp32, accumulated over the key blocks)
 //   warps 2-5 : softmax     one query row per thread: tcgen05.ld S -> running max / sum in the log2 domain ->
 //                           P_j (bf16 pairs) into TMEM with tcgen05.st: the A operand of the second MMA comes from TMEM, so
 //                           a block moves 48 KB through shared memory (Q, K, V reads + the TMA writes) instead of 80
@@ -26,9 +26,9 @@
 
 namespace b200 {
 
-constexpr int FA_BM = 128, FA_BN = 64, FA_STAGES = 3, FA_THREADS = 192;      // 3 stages: 97 KB per CTA, two CTAs fit one SM
+constexpr int FA_BM = 128, FA_BN = 64, FA_STAGES = 5, FA_THREADS = 192;      // 16 + 5 x 16 KB = 97 KB per CTA: two CTAs fit one SM
 constexpr uint32_t FA_Q_BYTES = FA_BM * 64 * 2, FA_KV_BYTES = FA_BN * 64 * 2;
-constexpr uint32_t FA_SMEM = FA_Q_BYTES + FA_STAGES * 2 * FA_KV_BYTES + 256;                // 16 + 48 KB + barriers
+constexpr uint32_t FA_SMEM = FA_Q_BYTES + FA_STAGES * 2 * FA_KV_BYTES + 256;                // 16 + 80 KB + barriers
 constexpr uint32_t FA_TMEM_COLS = 256;                     // S0 [0,64) S1 [64,128) O [128,192) P0 [192,224) P1 [224,256) (bf16 pairs)
 constexpr uint32_t FA_P_COL = 192;
 
@@ -42,6 +42,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) { float d; asm
 
 struct FaArgs {
     int n_q, n_k, n_kb;
+    unsigned long long* dbg;      // optional clock64 marks of CTA (0,0,0): [block][8] (softmax warp 2: 0-4, MMA thread: 5-7)
     bf16* O; long ldo, o_head_stride, o_batch_stride;
 };
 
@@ -61,8 +62,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     uint64_t* s_empty = s_full + 2;          // 2
     uint64_t* p_full = s_empty + 2;          // 2
     uint64_t* p_empty = p_full + 2;          // 2
-    uint64_t* pv_done = p_empty + 2;         // 1: completes once per PV_j
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
@@ -72,7 +72,6 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         mbar_init(q_full, 1);
         for (int s = 0; s < FA_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); mbar_init(&p_full[s], 4); mbar_init(&p_empty[s], 1); }
-        mbar_init(pv_done, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, FA_TMEM_COLS);
@@ -95,33 +94,46 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         }
     } else if (threadIdx.x == 32) {
         // ------------------------------ MMA issuer ------------------------------
+        // Per block this one thread performs four mbarrier waits, eight tcgen05.mma and three commits of 60-250 cycles each
+        // (tools/probe_attn.py prints the per-block timeline of CTA 0).  Splitting QK and PV between two issuing threads was
+        // measured slower: as a seventh warp it costs the softmax warps 40 registers (spills), as a second lane of this warp
+        // the two loops serialise.
         constexpr uint32_t idesc_qk = umma_idesc_bf16(FA_BM, FA_BN, 0, 0);        // A = Q (K-major), B = K_j (K-major)
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(FA_BM, 64, 0, 1);           // A = P (K-major), B = V_j (MN-major)
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(FA_BM, 64, 0, 1);           // A = P (TMEM), B = V_j (MN-major)
         const uint64_t dq = umma_desc_k128(smem_u32(sQ));
         mbar_wait(q_full, 0);
         auto issue_qk = [&](int j) {
             const int s = j % FA_STAGES, sb = j & 1;
+            const bool mk = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j > 0;
             mbar_wait(&kv_full[s], (j / FA_STAGES) & 1);
+            if (mk) a.dbg[(j - 1) * 16 + 8] = clock64();
             mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
+            if (mk) a.dbg[(j - 1) * 16 + 9] = clock64();
             tc_fence_after();
             const uint64_t dk = umma_desc_k128(smem_u32(sK + s * FA_KV_BYTES));
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(tmem + sb * FA_BN, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+            if (mk) a.dbg[(j - 1) * 16 + 10] = clock64();
             umma_commit(&s_full[sb]);
         };
         issue_qk(0);
         for (int j = 0; j < a.n_kb; ++j) {
+            const bool mk = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+            if (mk) a.dbg[j * 16 + 5] = clock64();
             if (j + 1 < a.n_kb) issue_qk(j + 1);                   // keep the tensor pipe busy while softmax_j runs
+            if (mk) a.dbg[j * 16 + 6] = clock64();
             const int s = j % FA_STAGES, sb = j & 1;
             mbar_wait(&p_full[sb], (j >> 1) & 1);
+            if (mk) a.dbg[j * 16 + 7] = clock64();
             tc_fence_after();
             const uint64_t dv = umma_desc_mn128(smem_u32(sV + s * FA_KV_BYTES), 8192);
 #pragma unroll
             for (int k = 0; k < 4; ++k)                            // 16 keys per MMA: 8 TMEM columns of P (bf16 pairs), +2 x 1024 B in V
                 umma_bf16_ts(tmem + 2 * FA_BN, tmem + FA_P_COL + sb * 32 + k * 8, dv + 128 * k, idesc_pv, (j | k) != 0);
-            umma_commit(pv_done);
+            if (mk) a.dbg[j * 16 + 11] = clock64();
             umma_commit(&kv_empty[s]);
             umma_commit(&p_empty[sb]);
+            if (mk) a.dbg[j * 16 + 12] = clock64();
         }
     } else if (warp >= 2) {
         // ------------------------------ softmax / output ------------------------------
@@ -133,12 +145,16 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         float m = -INFINITY, l = 0.f;
         for (int j = 0; j < a.n_kb; ++j) {
             const int sb = j & 1;
+            const bool mk = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
+            if (mk) a.dbg[j * 16 + 0] = clock64();
             mbar_wait(&s_full[sb], (j >> 1) & 1);
+            if (mk) a.dbg[j * 16 + 1] = clock64();
             tc_fence_after();
             uint32_t r0[32], r1[32];
             tmem_ld_32x32(lane_addr + sb * FA_BN, r0);
             tmem_ld_32x32(lane_addr + sb * FA_BN + 32, r1);
             tmem_ld_wait();
+            if (mk) a.dbg[j * 16 + 2] = clock64();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[sb]);
@@ -162,7 +178,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
                 const float alpha = ex2_approx((m - mnew) * LOG2E);
                 m = mnew;
                 l *= alpha;
-                mbar_wait(pv_done, (j - 1) & 1);                   // PV_0 .. PV_{j-1} have landed in O
+                mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);   // PV_{j-1} (and with it PV_0 .. PV_{j-2}) has landed in O
                 tc_fence_after();
                 uint32_t q0r[32], q1r[32];
                 tmem_ld_32x32(lane_addr + 2 * FA_BN, q0r);
@@ -181,18 +197,17 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             const float m2 = m * LOG2E;
             float sum4[4] = {0.f, 0.f, 0.f, 0.f};
             mbar_wait(&p_empty[sb], ((j >> 1) & 1) ^ 1);           // PV_{j-2} no longer reads this P buffer
+            if (mk) a.dbg[j * 16 + 3] = clock64();
             uint32_t pk[32];                                       // P_j as bf16 pairs: the A operand of PV_j, read from TMEM
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float pa = ex2_approx(fmaf(__uint_as_float(r0[i]), LOG2E, -m2));
-                const float pb = ex2_approx(fmaf(__uint_as_float(r1[i]), LOG2E, -m2));
-                sum4[i & 3] += pa + pb;
-                r0[i] = __float_as_uint(pa); r1[i] = __float_as_uint(pb);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                pk[i] = pack_bf16(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
-                pk[16 + i] = pack_bf16(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1]));
+            for (int i = 0; i < 16; ++i) {                         // exp2 and pack pair by pair: a score register dies as its pair is packed
+                const float pa = ex2_approx(fmaf(__uint_as_float(r0[2 * i]), LOG2E, -m2));
+                const float pb = ex2_approx(fmaf(__uint_as_float(r0[2 * i + 1]), LOG2E, -m2));
+                const float pc = ex2_approx(fmaf(__uint_as_float(r1[2 * i]), LOG2E, -m2));
+                const float pd = ex2_approx(fmaf(__uint_as_float(r1[2 * i + 1]), LOG2E, -m2));
+                sum4[i & 3] += (pa + pb) + (pc + pd);
+                pk[i] = pack_bf16(pa, pb);
+                pk[16 + i] = pack_bf16(pc, pd);
             }
             tmem_st_32x32(lane_addr + FA_P_COL + sb * 32, pk);
             tmem_st_wait();
@@ -200,10 +215,11 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[sb]);
+            if (mk) a.dbg[j * 16 + 4] = clock64();
         }
         {
             uint32_t r0[32], r1[32];
-            mbar_wait(pv_done, (a.n_kb - 1) & 1);
+            mbar_wait(&p_empty[(a.n_kb - 1) & 1], ((a.n_kb - 1) >> 1) & 1);   // the last PV has landed
             tc_fence_after();
             tmem_ld_32x32(lane_addr + 2 * FA_BN, r0);
             tmem_ld_32x32(lane_addr + 2 * FA_BN + 32, r1);
@@ -264,6 +280,8 @@ static const CUtensorMap* fa_map(const bf16* base, long ld, long head_stride, lo
     return &g_fa_maps.emplace(key, m).first->second;
 }
 
+unsigned long long* g_fa_dbg = nullptr;      // tests: clock marks of CTA (0,0,0) (b200TestAttentionTimeline)
+
 void attention_tc(const AttnParams& p, cudaStream_t s) {
     if (p.mask || p.qk_dump) { attention_simt(p, s); return; }     // masks / QK dumps only exist on the 256-row prefill path
     const CUtensorMap* mq = fa_map(p.Q, p.ldq, p.q_head_stride, p.q_batch_stride, p.n_q, p.n_head, p.batch, FA_BM);
@@ -272,6 +290,7 @@ void attention_tc(const AttnParams& p, cudaStream_t s) {
     if (!mq || !mk || !mv) return;
     FaArgs a;
     a.n_q = p.n_q; a.n_k = p.n_k; a.n_kb = cdiv(p.n_k, FA_BN);
+    a.dbg = g_fa_dbg;
     a.O = p.O; a.ldo = p.ldo; a.o_head_stride = p.o_head_stride; a.o_batch_stride = p.o_batch_stride;
     constexpr size_t smem = FA_SMEM + 1024 + 256;
     static bool attr = false;
