@@ -275,7 +275,10 @@ void decode_free_lanes() {                 // called when the decoder is closed 
     }
 }
 
-struct DecodeJob { int n_initial, nb, k, sample_len, sot_index, steps; bool done; StepGraph* graph; };
+struct DecodeJob { int n_initial, nb, k, sample_len, sot_index, steps; bool done; StepGraph* graph; int issued = 0, checked = 0; };
+// completion is polled one round behind the issue front: round r + 1 is already queued when the host waits for round r's flag,
+// so the GPU never idles while the host synchronises and relaunches (rounds issued past the end are no-ops)
+static cudaEvent_t g_round_ev[MAX_LANES][2];
 
 // state + prefill + first sampling step of the ACTIVE lane, all on `st` (the prefill workspaces are shared by the lanes)
 static void decode_begin(DecodeJob& j, const int* initial_tokens, int beam_size, int without_timestamps, int max_initial_timestamp_index) {
@@ -347,7 +350,11 @@ static void decode_issue(DecodeJob& j) {
         else for (int i = 0; i < GRAPH_STEPS; ++i) one_step(j.nb, j.k);
         j.steps += GRAPH_STEPS;
     }
-    B200_CHECK(cudaMemcpyAsync(c.pin_done, &c.st->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaMemcpyAsync(c.pin_done + (j.issued & 1), &c.st->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+    cudaEvent_t& ev = g_round_ev[g_active_lane][j.issued & 1];
+    if (!ev) B200_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    B200_CHECK(cudaEventRecord(ev, st));
+    ++j.issued;
 }
 
 // finalize (decoding.py:411-431 / :320-325) of the ACTIVE lane; its stream must be idle
@@ -441,13 +448,18 @@ int b200DecodeWindows(const int* windows, int n_windows, const int* initial_toke
             // ---- steps: every lane advances GRAPH_STEPS per round; completion is polled once per round ----
             bool any = true;
             while (any) {
-                for (int i = 0; i < n; ++i) if (!job[i].done && job[i].steps < sample_len) { activate_lane(i); decode_issue(job[i]); }
+                for (int i = 0; i < n; ++i)
+                    while (!job[i].done && job[i].steps < sample_len && job[i].issued - job[i].checked < 2) { activate_lane(i); decode_issue(job[i]); }
                 any = false;
                 for (int i = 0; i < n; ++i) {
                     if (job[i].done) continue;
                     activate_lane(i);
-                    B200_CHECK(cudaStreamSynchronize(S().stream));
-                    if (*g_dc.pin_done != 0 || job[i].steps >= sample_len) job[i].done = true; else any = true;
+                    if (job[i].checked < job[i].issued) {
+                        B200_CHECK(cudaEventSynchronize(g_round_ev[i][job[i].checked & 1]));
+                        const int flag = g_dc.pin_done[job[i].checked & 1];
+                        ++job[i].checked;
+                        if (flag != 0 || (job[i].steps >= sample_len && job[i].checked == job[i].issued)) job[i].done = true; else any = true;
+                    } else job[i].done = true;                          // nothing in flight and nothing left to issue
                 }
             }
             for (int i = 1; i < n; ++i) { activate_lane(i); B200_CHECK(cudaEventRecord(ev_join[i], S().stream)); B200_CHECK(cudaStreamWaitEvent(main_stream, ev_join[i], 0)); }
