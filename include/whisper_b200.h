@@ -167,6 +167,9 @@ void b200TestGemm(const void* dA, const void* dB, const float* dBias, void* dC, 
 void b200TestGemmTile(int sel);
 /* Average device time in ms of `iters` back-to-back tcgen05 GEMMs; mode bits: 1 bias, 2 GELU, 4 fp32 output + fp32 residual. */
 float b200TestGemmTime(const void* dA, const void* dB, void* dC, int M, int N, int K, int mode, int iters);
+/* clock64 marks of CTA 0 of one tcgen05 GEMM launch, out[tile * 16 + k]: epilogue warp 2: 0 entered, 1 accumulator ready,
+ * 2+3c / 3+3c / 4+3c loads of chunk c issued / landed / chunk done, 14 accumulator released; 15 = MMA thread: tile issued. */
+int b200TestGemmTimeline(const void* dA, const void* dB, void* dC, int M, int N, int K, int mode, unsigned long long* out, int cap_tiles);
 /* State read-back as fp32 HOST arrays in the reference's layouts: Xa (1500, d) of window w;
  * CK (Ld,H,64,1500) / CV (Ld,H,1500,64) of window w; logical KV cache rows (2Ld, bs, n_rows, d). */
 void b200TestGetXa(float* out, int w);

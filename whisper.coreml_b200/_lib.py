@@ -49,6 +49,7 @@ SIGNATURES = {
     # test hooks
     "b200TestGemm": (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
     "b200TestGemmTile": (None, [c_int]),
+    "b200TestGemmTimeline": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int]),
     "b200TestGemmTime": (ctypes.c_float, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "b200TestGetXa": (None, [f32p, c_int]),
     "b200TestGetCrossKV": (None, [f32p, f32p, c_int]),

@@ -51,6 +51,38 @@ extern "C" float b200TestGemmTime(const void* dA, const void* dB, void* dC, int 
     return ms / (iters > 0 ? iters : 1);
 }
 
+// clock64 marks of CTA 0 of one GEMM launch (mode bits as b200TestGemmTime), out[tile * 16 + k]: epilogue warp 2: 0 tile
+// entered, 1 accumulator ready, 2+3c / 3+3c / 4+3c chunk c loads issued / landed / chunk done, 14 accumulator released;
+// 15 = MMA thread: last MMA of the tile issued.  Returns the number of tiles CTA 0 processed.
+namespace b200 { extern unsigned long long* g_gemm_dbg; }
+extern "C" int b200TestGemmTimeline(const void* dA, const void* dB, void* dC, int M, int N, int K, int mode, unsigned long long* out, int cap_tiles) {
+    GemmParams p = gemm_plain((const bf16*)dA, (const bf16*)dB, dC, M, N, K);
+    float *bias = nullptr, *add = nullptr, *cf = nullptr;
+    if (mode & 1) { cudaMalloc(&bias, (size_t)N * 4); cudaMemset(bias, 0, (size_t)N * 4); p.bias = bias; }
+    p.gelu = (mode & 2) ? 1 : 0;
+    if (mode & 4) {
+        cudaMalloc(&add, (size_t)M * N * 4); cudaMemset(add, 0, (size_t)M * N * 4);
+        cudaMalloc(&cf, (size_t)M * N * 4);
+        p.add = add; p.add_rows = M; p.ld_add = N; p.C = cf; p.c_fp32 = 1;
+    }
+    unsigned long long* d = nullptr;
+    cudaMalloc(&d, (size_t)cap_tiles * 16 * 8); cudaMemset(d, 0, (size_t)cap_tiles * 16 * 8);
+    for (int i = 0; i < 2; ++i) gemm_tcgen05(p, 0);
+    g_gemm_dbg = d;
+    gemm_tcgen05(p, 0);
+    g_gemm_dbg = nullptr;
+    B200_CHECK(cudaStreamSynchronize(0));
+    B200_CHECK(cudaMemcpy(out, d, (size_t)cap_tiles * 16 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    if (bias) cudaFree(bias);
+    if (add) cudaFree(add);
+    if (cf) cudaFree(cf);
+    const int tiles = ((M + 127) / 128) * ((N + 255) / 256);
+    int n = 0;
+    for (int t = 0; t < tiles; t += 148) ++n;
+    return n < cap_tiles ? n : cap_tiles;
+}
+
 // ---- state read-back hooks (tests only) ---------------------------------------------------------
 #include <vector>
 #include "state.cuh"

@@ -42,35 +42,105 @@ struct GemmKernelArgs {
     bf16* C2; long c2_batch_stride; int c2_heads, c2_keys;
     int vec_ok;                 // output / residual rows are 16-byte aligned: 128-bit epilogue accesses allowed
     int dbg_skip;               // experiments (B200_GEMM_SKIP): 1 = epilogue without global stores, 2 = no epilogue at all
+    unsigned long long* dbg;    // optional clock64 marks of CTA 0 (b200TestGemmTimeline): [tile][16]
 };
 
 // Epilogue of one 128-row x BLOCK_N accumulator tile: the calling warp owns TMEM lanes [quad * 32, +32) (tmem_acc already
-// points at them) and the 32-column chunks half, half + 2, ... (the two warps of a quadrant write the two 64-byte halves of a
-// bf16 output line at about the same time); thread <-> output row t.  INFLIGHT chunks are loaded per tcgen05.wait::ld:
-// measured on the encoder's shapes, 1 is fastest (2 and 4 were 10-40 % slower: the bursts of stores that follow a larger
-// batch of loads compete with the next tile's operand reads for the shared-memory / L1 data path).
+// points at them) and the 64-column units half, half + 2, ...; thread <-> output row t in the TMEM layout.
+//
+// Stores are coalesced through a 4 KB transposition buffer per warp.  In the TMEM layout a warp store instruction writes 16
+// bytes of each of 32 rows; the LSU retires such an instruction piece by piece (~4 cycles per 16-byte piece, measured with
+// b200TestGemmTimeline: 15 000 cycles to store one 128 x 256 bf16 tile, twice the K = 1280 main loop), and the epilogue, not
+// the MMAs, paced the GEMMs.  After the transposition lane l handles 16 bytes of the rows 4 i + (l >> 3), so an instruction
+// writes (and, for the fp32 residual, reads) four whole 128-byte row segments.
+//   bf16 outputs: a 64-column unit at once (two tcgen05.ld in flight, 128 bytes per row);
+//   fp32 outputs: the unit's two 32-column chunks one after the other (128 bytes per row each).
+// Chunks that are not fully inside N, or that also feed the fragment-major second output, keep the direct path.
 template <int BLOCK_N, int INFLIGHT>
 __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& g, uint32_t tmem_acc, int half, int lane, int n_blk, int b, int t,
-                                              bool row_ok, long c_row, const float* add_row, float4* stage) {
+                                              bool row_ok, long c_row, const float* add_row, float4* stage, unsigned long long* mk) {
     if (g.dbg_skip == 2) return;
-    constexpr int NSUB = BLOCK_N / 64;                  // 32-column sub-chunks of this warp
-    constexpr int NF = INFLIGHT < NSUB ? INFLIGHT : NSUB;
+    constexpr int NUNIT = BLOCK_N / 128;                // 64-column units of this warp
+    constexpr int NF = 1;
+    const int sub = lane >> 3, ch = lane & 7;
 #pragma unroll 1
-    for (int s0 = 0; s0 < NSUB; s0 += NF) {
+    for (int k = 0; k < NUNIT; ++k) {
+    const int u64 = half + 2 * k;
+    const int nU = n_blk * BLOCK_N + u64 * 64;
+    if (!g.c_fp32 && !g.C2 && g.vec_ok && nU + 64 <= g.N && g.dbg_skip == 0) {
+        // ---- bf16, coalesced: the whole 64-column unit ----
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(tmem_acc + u64 * 64, ra);
+        tmem_ld_32x32(tmem_acc + u64 * 64 + 32, rb);
+        const float bva = g.bias ? __ldg(g.bias + nU + lane) : 0.f, bvb = g.bias ? __ldg(g.bias + nU + 32 + lane) : 0.f;
+        if (mk) mk[2 + 6 * k] = clock64();
+        tmem_ld_wait();
+        if (mk) mk[3 + 6 * k] = clock64();
+        uint4* st16 = reinterpret_cast<uint4*>(stage);          // [32 rows][8 x 16 bytes], 16-byte index ^= row & 7
+        if (g.bias) {
+            // bias: lane i loaded column nU + i (+ 32); every thread needs all 64.  Broadcast through the staging buffer with
+            // 128-bit shared loads (16 per unit) - as 64 shuffles per unit the bias add alone cost 10 % of the QKV GEMM
+            float* sb = reinterpret_cast<float*>(stage);
+            sb[lane] = bva; sb[32 + lane] = bvb;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 ba = reinterpret_cast<const float4*>(sb)[i], bb = reinterpret_cast<const float4*>(sb)[8 + i];
+                ra[4 * i] = __float_as_uint(__uint_as_float(ra[4 * i]) + ba.x); ra[4 * i + 1] = __float_as_uint(__uint_as_float(ra[4 * i + 1]) + ba.y);
+                ra[4 * i + 2] = __float_as_uint(__uint_as_float(ra[4 * i + 2]) + ba.z); ra[4 * i + 3] = __float_as_uint(__uint_as_float(ra[4 * i + 3]) + ba.w);
+                rb[4 * i] = __float_as_uint(__uint_as_float(rb[4 * i]) + bb.x); rb[4 * i + 1] = __float_as_uint(__uint_as_float(rb[4 * i + 1]) + bb.y);
+                rb[4 * i + 2] = __float_as_uint(__uint_as_float(rb[4 * i + 2]) + bb.z); rb[4 * i + 3] = __float_as_uint(__uint_as_float(rb[4 * i + 3]) + bb.w);
+            }
+            __syncwarp();                               // every lane has read the bias before the buffer is overwritten
+        }
+        if (g.gelu == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                ra[i] = __float_as_uint(gelu_erf_fit(__uint_as_float(ra[i])));
+                rb[i] = __float_as_uint(gelu_erf_fit(__uint_as_float(rb[i])));
+            }
+        } else if (g.gelu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                ra[i] = __float_as_uint(gelu_erf(__uint_as_float(ra[i])));
+                rb[i] = __float_as_uint(gelu_erf(__uint_as_float(rb[i])));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(ra[8 * i]), __uint_as_float(ra[8 * i + 1])); w.y = pack_bf16(__uint_as_float(ra[8 * i + 2]), __uint_as_float(ra[8 * i + 3]));
+            w.z = pack_bf16(__uint_as_float(ra[8 * i + 4]), __uint_as_float(ra[8 * i + 5])); w.w = pack_bf16(__uint_as_float(ra[8 * i + 6]), __uint_as_float(ra[8 * i + 7]));
+            st16[lane * 8 + (i ^ (lane & 7))] = w;
+            w.x = pack_bf16(__uint_as_float(rb[8 * i]), __uint_as_float(rb[8 * i + 1])); w.y = pack_bf16(__uint_as_float(rb[8 * i + 2]), __uint_as_float(rb[8 * i + 3]));
+            w.z = pack_bf16(__uint_as_float(rb[8 * i + 4]), __uint_as_float(rb[8 * i + 5])); w.w = pack_bf16(__uint_as_float(rb[8 * i + 6]), __uint_as_float(rb[8 * i + 7]));
+            st16[lane * 8 + ((4 + i) ^ (lane & 7))] = w;
+        }
+        __syncwarp();
+        const long col = (g.c_split ? (long)(nU >> 6) * g.c_split_stride : (long)nU) + 8 * ch;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + sub;
+            const uint4 x = st16[rr * 8 + (ch ^ (rr & 7))];
+            if (t - lane + rr < g.rows_per_batch)
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(g.C) + (c_row - lane + rr) * g.ldc + col) = x;
+        }
+        __syncwarp();                                   // the next unit overwrites the staging buffer
+        if (mk) mk[4 + 6 * k] = clock64();
+        continue;
+    }
+#pragma unroll 1
+    for (int s0 = 0; s0 < 2; ++s0) {
+    const int cidx = 2 * u64 + s0;                      // 32-column chunk of the tile
     uint32_t r[NF][32];
 #pragma unroll
-    for (int u = 0; u < NF; ++u) tmem_ld_32x32(tmem_acc + (half + 2 * (s0 + u)) * 32, r[u]);
-    // the bias and residual loads of the chunk are issued BEFORE the wait for the TMEM load: their L2 latency was on the
-    // epilogue's critical path four times per tile.  fp32 chunks that lie fully inside N take the coalesced path (`tp`): the
-    // 32 x 32 chunk is transposed through 4 KB of shared memory per warp so that a warp instruction reads (residual) and
-    // writes four whole 128-byte row segments instead of 16 bytes of each of 32 rows; there lane l handles columns
-    // 4 (l & 7) .. + 3 of the rows 4 i + (l >> 3).  (Measured: out-projection 24.7 -> 18.6 us; for bf16 outputs the extra
-    // shared-memory traffic slowed the main loop more than the stores gained - MLP1 59 -> 67 us - so they store directly.)
-    const int sub = lane >> 3, ch = lane & 7;
+    for (int u = 0; u < NF; ++u) tmem_ld_32x32(tmem_acc + cidx * 32, r[u]);
+    // the bias and residual loads of the chunk are issued BEFORE the wait for the TMEM load (their L2 latency was on the
+    // epilogue's critical path four times per tile)
     float bvs[NF]; float4 qs[NF][8];
 #pragma unroll
     for (int u = 0; u < NF; ++u) {
-        const int n0 = n_blk * BLOCK_N + (half + 2 * (s0 + u)) * 32;
+        const int n0 = n_blk * BLOCK_N + cidx * 32;
         bvs[u] = (g.bias && n0 + lane < g.N) ? __ldg(g.bias + n0 + lane) : 0.f;   // lane i holds column n0 + i; broadcast by shuffle below
         const bool tp = g.vec_ok && n0 + 32 <= g.N && !g.C2 && g.c_fp32;
         if (add_row && tp) {
@@ -84,10 +154,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& g, uint32_t 
             for (int i = 0; i < 8; ++i) qs[u][i] = *reinterpret_cast<const float4*>(add_row + n0 + 4 * i);
         }
     }
+    if (mk) mk[2 + 6 * k + 3 * s0] = clock64();
     tmem_ld_wait();
+    if (mk) mk[3 + 6 * k + 3 * s0] = clock64();
 #pragma unroll
     for (int u = 0; u < NF; ++u) {
-        const int n0 = n_blk * BLOCK_N + (half + 2 * (s0 + u)) * 32;
+        const int n0 = n_blk * BLOCK_N + cidx * 32;
         if (n0 >= g.N) continue;                        // warp uniform
         const bool full = g.vec_ok && n0 + 32 <= g.N;
         const float bv = bvs[u];
@@ -184,6 +256,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& g, uint32_t 
             }
         }
     }
+    if (mk) mk[4 + 6 * k + 3 * s0] = clock64();
+    }
     }
 }
 
@@ -259,6 +333,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
             umma_commit(&tmem_full[a]);                     // accumulator ready for the epilogue
+            if (g.dbg && blockIdx.x == 0) g.dbg[(size_t)(tile / gridDim.x) * 16 + 15] = clock64();
             if (++a == 2) { a = 0; aph ^= 1; }
         }
     } else if (warp >= 2) {
@@ -275,12 +350,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             const long c_row = (long)b * g.c_batch_rows + g.c_row0 + t;
             const long m_flat = (long)b * g.rows_per_batch + t;
             const float* add_row = g.add ? g.add + (m_flat % g.add_rows) * g.ld_add : nullptr;
+            unsigned long long* mk = (g.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) ? g.dbg + (size_t)(tile / gridDim.x) * 16 : nullptr;
+            if (mk) mk[0] = clock64();
             mbar_wait(&tmem_full[a], aph);
+            if (mk) mk[1] = clock64();
             tc_fence_after();
-            epilogue_tile<BLOCK_N, INFLIGHT>(g, tmem_base + ((uint32_t)(quad * 32) << 16) + a * BLOCK_N, half, lane, n_blk, b, t, row_ok, c_row, add_row, stage);
+            epilogue_tile<BLOCK_N, INFLIGHT>(g, tmem_base + ((uint32_t)(quad * 32) << 16) + a * BLOCK_N, half, lane, n_blk, b, t, row_ok, c_row, add_row, stage, mk);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[a]);
+            if (mk) mk[14] = clock64();
             if (++a == 2) { a = 0; aph ^= 1; }
         }
     }
@@ -397,7 +476,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid
             const float* add_row = g.add ? g.add + (m_flat % g.add_rows) * g.ld_add : nullptr;
             mbar_wait(&tmem_full[a], aph);
             tc_fence_after();
-            epilogue_tile<PAIR_N, INFLIGHT>(g, tmem_base + ((uint32_t)(quad * 32) << 16) + a * PAIR_N, half, lane, n_blk, b, t, row_ok, c_row, add_row, stage);
+            epilogue_tile<PAIR_N, INFLIGHT>(g, tmem_base + ((uint32_t)(quad * 32) << 16) + a * PAIR_N, half, lane, n_blk, b, t, row_ok, c_row, add_row, stage, nullptr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[a]), 0));
@@ -469,6 +548,7 @@ static const CUtensorMap* cached_map(const void* base, int rank, const uint64_t*
 void gemm_clear_map_cache() { g_map_cache.clear(); }
 
 static int g_num_sms = 0;
+unsigned long long* g_gemm_dbg = nullptr;    // tests: clock marks of CTA 0 (b200TestGemmTimeline)
 
 // BLOCK_N == 0 selects the CTA-pair kernel (256 x 256 tiles)
 template <int BLOCK_N, int STAGES, int INFLIGHT>
@@ -501,6 +581,7 @@ static void launch(const GemmParams& p, cudaStream_t stream) {
                (!p.add || (((p.ld_add * 4) % 16 == 0) && (((uintptr_t)p.add) % 16 == 0)));
 
     { static int ex = -1; if (ex < 0) { const char* e = getenv("B200_GELU_EXACT"); ex = e ? atoi(e) : 0; } if (g.gelu && ex) g.gelu = 2; }
+    g.dbg = g_gemm_dbg;
     { static int skip = -1; if (skip < 0) { const char* e = getenv("B200_GEMM_SKIP"); skip = e ? atoi(e) : 0; } g.dbg_skip = skip; }
     if (!g_num_sms) {
         int dev = 0;
