@@ -254,10 +254,10 @@ def main():
         ach = by / (per_step_ms * 1e-3) / 1e9
         lanes = min(int(os.environ.get("B200_DECODE_LANES", "8")), 8, n_windows)
         out["roofline"] = {"kernel": "decoder_mega_kernel: one persistent launch per decoder1 token step (LN + 7 GEMVs per layer, self / "
-                                     "cross attention, vocabulary projection) + the 2 sampling kernels that follow it",
+                                     "cross attention, vocabulary projection) + the sampling kernel that follows it",
                            "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                           # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_decoder_mega_v2_ncu_full.csv (t ~ 10)
-                           "traffic": 356.2e6,
+                           # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_decoder_mega_r1f_ncu_full.csv (t ~ 10)
+                           "traffic": 354.0e6,
                            "peak_source": which, "bytes_per_step": by, "us_per_step": per_step_ms * 1e3, "steps": dec_steps,
                            "lanes": lanes,
                            "note": f"algorithmic bytes of one token step of one window (SURVEY 8d formula at the mean text_offset) divided by "
