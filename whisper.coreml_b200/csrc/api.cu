@@ -315,7 +315,8 @@ bool run_step_mega(int nb, int text_offset, const float* d_mask, const float* d_
     uint2* p = s.mega_ll;                                               // carved in the order of mega_ll_words()
     a.ll_qkv = p; p += B * 3 * d; a.ll_att = p; p += B * d / 2; a.ll_catt = p; p += B * d / 2;
     a.ll_x1 = p; p += B * d; a.ll_x2 = p; p += B * d; a.ll_x3 = p; p += B * d; a.ll_q = p; p += B * d;
-    a.ll_cap = p; p += (size_t)s.H * 7 * 8 * 66; a.ll_hid = p;
+    a.ll_cap = p; p += (size_t)s.H * 7 * 8 * 66; a.ll_hid = p; p += B * 2 * d;
+    a.ll_x1b = p; p += B * d / 2; a.ll_x2b = p; p += B * d / 2; a.ll_x3b = p;
     a.logits = s.slogits; a.ld_logits = s.V; a.table = s.table; a.mkv = s.mkv; a.kv_stride = (long)s.bs * N_TEXT_CTX * s.d;
     a.mask = d_mask; a.x_in = d_x_in; a.text_offset = text_offset; a.barrier = s.mega_barrier; a.seq = s.mega_barrier + 2; a.dbg = s.mega_dbg;
     static const int force_ctas = getenv("B200_MEGA_CTAS") ? atoi(getenv("B200_MEGA_CTAS")) : 0;      // experiments: fixed grid size
@@ -325,7 +326,7 @@ size_t mega_ll_words_for(size_t d, size_t H);
 static size_t mega_ll_words(size_t d, size_t H) { return mega_ll_words_for(d, H); }
 size_t mega_ll_words_for(size_t d, size_t H) {
     const size_t B = STEP_MAX_BEAMS;
-    return B * 3 * d + 2 * (B * d / 2) + 4 * B * d + H * 7 * 8 * 66 + B * 2 * d;
+    return B * 3 * d + 2 * (B * d / 2) + 4 * B * d + H * 7 * 8 * 66 + B * 2 * d + 3 * (B * d / 2);
 }
 
 // =================================================================================================

@@ -130,6 +130,18 @@ __device__ __forceinline__ void ll_load2x5(LL5& r, const uint2* p0, const uint2*
           "=l"(r.w[4][0]), "=l"(r.w[4][1])
         : "l"(p0), "l"(p1), "l"(p2), "l"(p3), "l"(p4) : "memory");
 }
+// five 8-byte LL loads from one asm statement (see ll_load2x5)
+struct L5 { u64 w[5]; };
+__device__ __forceinline__ void ll_load1x5(L5& r, const uint2* p0, const uint2* p1, const uint2* p2, const uint2* p3, const uint2* p4) {
+    asm volatile(
+        "ld.relaxed.gpu.global.u64 %0, [%5];\n\t"
+        "ld.relaxed.gpu.global.u64 %1, [%6];\n\t"
+        "ld.relaxed.gpu.global.u64 %2, [%7];\n\t"
+        "ld.relaxed.gpu.global.u64 %3, [%8];\n\t"
+        "ld.relaxed.gpu.global.u64 %4, [%9];"
+        : "=l"(r.w[0]), "=l"(r.w[1]), "=l"(r.w[2]), "=l"(r.w[3]), "=l"(r.w[4])
+        : "l"(p0), "l"(p1), "l"(p2), "l"(p3), "l"(p4) : "memory");
+}
 // Reads an LL matrix of n_rows x row_items 16-byte items (2 words each) and hands every item to f(row, c, word0, word1).
 // A thread owns items c = tid + 128 i (i < 5) of every row; two rows (10 loads) are in flight per round, and nothing is
 // stored before the round's loads have all returned.  Items beyond row_items / n_rows re-read item 0 and are dropped.
@@ -204,6 +216,7 @@ struct GemvStage {
     const float* bias;          // [N] or nullptr
     int res_mode; const uint2* res_ll; uint32_t res_epoch;      // residual: LL fp32 [nb][ld_out]
     uint2* out_ll; float* out_f32; long ld_out;
+    uint2* out_llb;             // EPI_LL_F32: the same outputs again as bf16x2 LL words (LayerNorm input of the next stage) or nullptr
     int n_valid;                // outputs >= n_valid are not stored
     uint32_t epoch;
 };
@@ -260,9 +273,14 @@ __device__ __forceinline__ void stage_gemv(const MegaSmem& sm, Ring& ring, int& 
                 v = gelu_erf(v);
                 const float nxt = __shfl_down_sync(0xffffffffu, v, 1);          // lanes are (ob, orow): orow + 1 is the next lane
                 if (owner && !(orow & 1)) ll_store(g.out_ll + ((long)ob * g.ld_out + n) / 2, pack_bf16(v, nxt), g.epoch);
+            } else if (g.epi == EPI_LL_F32) {
+                if (owner) ll_store(g.out_ll + (long)ob * g.ld_out + n, __float_as_uint(v), g.epoch);
+                if (g.out_llb) {                                      // (stage uniform)
+                    const float nxt = __shfl_down_sync(0xffffffffu, v, 1);
+                    if (owner && !(orow & 1)) ll_store(g.out_llb + ((long)ob * g.ld_out + n) / 2, pack_bf16(v, nxt), g.epoch);
+                }
             } else if (owner) {
-                if (g.epi == EPI_LL_F32) ll_store(g.out_ll + (long)ob * g.ld_out + n, __float_as_uint(v), g.epoch);
-                else __stcg(g.out_f32 + (long)ob * g.ld_out + n, v);
+                __stcg(g.out_f32 + (long)ob * g.ld_out + n, v);
             }
         }
         red_buf ^= 1;                                 // the next unit reduces through the other buffer: one barrier per unit
@@ -347,35 +365,37 @@ __device__ __forceinline__ void prologue_ln(const MegaSmem& sm, Ring& ring, cons
             row_done(b, s1, s2);
         }
     } else {
-        ll_wait_sentinels(x_ll, epoch, d, 16, false, a.nb, tid, 12);       // written by 16-column GEMV tiles
+        // x_ll holds bf16x2 LL words here (one word = one 2-column item): half the bytes of the fp32 residual words, and all
+        // rows of up to five beams fit one round of loads (25 x 8 bytes in flight per thread) instead of two
+        ll_wait_sentinels(x_ll, epoch, d >> 1, 8, false, a.nb, tid, 12);   // written by 16-column GEMV tiles (8 words)
         dbg.cyc(db + 2);
 #pragma unroll 1
-        for (int r0 = 0; r0 < a.nb; r0 += MG_LN_ROWS) {                    // MG_LN_ROWS rows (5 loads each) in flight per round
-            LL5 rr[MG_LN_ROWS];
-            const uint2* pr[MG_LN_ROWS];
+        for (int r0 = 0; r0 < a.nb; r0 += 5) {
+            L5 rr[5];
+            const uint2* pr[5];
 #pragma unroll
-            for (int q = 0; q < MG_LN_ROWS; ++q) pr[q] = x_ll + 2L * min(r0 + q, a.nb - 1) * row_items;     // rows past nb re-read the last row
+            for (int q = 0; q < 5; ++q) pr[q] = x_ll + (long)min(r0 + q, a.nb - 1) * row_items;     // rows past nb re-read the last row
             unsigned spins = 0;
             bool ok;
             do {
 #pragma unroll
-                for (int q = 0; q < MG_LN_ROWS; ++q) ll_load2x5(rr[q], pr[q] + 2 * cc[0], pr[q] + 2 * cc[1], pr[q] + 2 * cc[2], pr[q] + 2 * cc[3], pr[q] + 2 * cc[4]);
+                for (int q = 0; q < 5; ++q) ll_load1x5(rr[q], pr[q] + cc[0], pr[q] + cc[1], pr[q] + cc[2], pr[q] + cc[3], pr[q] + cc[4]);
                 ok = true;
 #pragma unroll
-                for (int q = 0; q < MG_LN_ROWS; ++q)
+                for (int q = 0; q < 5; ++q)
 #pragma unroll
-                    for (int i = 0; i < MG_IPR; ++i) ok = ok & ll_ok(rr[q].w[i][0], epoch) & ll_ok(rr[q].w[i][1], epoch);
+                    for (int i = 0; i < MG_IPR; ++i) ok = ok & ll_ok(rr[q].w[i], epoch);
                 if (!ok) ll_backoff(spins, 2);
             } while (!ok);
 #pragma unroll
-            for (int q = 0; q < MG_LN_ROWS; ++q) {
+            for (int q = 0; q < 5; ++q) {
                 if (r0 + q < a.nb) {                                   // warp uniform
                     float2* dst = reinterpret_cast<float2*>(sm.xs + (long)(r0 + q) * sm.ldx + d);
                     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                     for (int i = 0; i < MG_IPR; ++i)
                         if (v[i]) {
-                            const float x = __uint_as_float((uint32_t)rr[q].w[i][0]), y = __uint_as_float((uint32_t)rr[q].w[i][1]);
+                            const float x = bf16lo((uint32_t)rr[q].w[i]), y = bf16hi((uint32_t)rr[q].w[i]);
                             dst[cc[i]] = make_float2(x, y);
                             s1 += x + y; s2 = fmaf(x, x, fmaf(y, y, s2));
                         }
@@ -823,19 +843,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decoder_mega_kernel(const __gri
             continue;
         }
         const StageDesc sd = stage_desc(st, l < M.Ld ? l : 0, cta, nctas);
-        GemvStage g{sd.n_tiles, sd.n_kc, sd.vcta, EPI_LL_F32, nullptr, RES_NONE, nullptr, ep, nullptr, nullptr, (long)d, d, ep};
+        GemvStage g{sd.n_tiles, sd.n_kc, sd.vcta, EPI_LL_F32, nullptr, RES_NONE, nullptr, ep, nullptr, nullptr, (long)d, nullptr, d, ep};
         const uint2* pro_src = nullptr; uint32_t pro_ep = ep;
         switch (st) {
-        case ST_QKV: pro_src = a.ll_x3; pro_ep = ep_prev; g.bias = L.qkv_b; g.out_ll = a.ll_qkv; g.ld_out = 3L * d; g.n_valid = 3 * d; break;
+        case ST_QKV: pro_src = a.ll_x3b; pro_ep = ep_prev; g.bias = L.qkv_b; g.out_ll = a.ll_qkv; g.ld_out = 3L * d; g.n_valid = 3 * d; break;
         case ST_OUT:
-            pro_src = a.ll_att; g.bias = L.attn_out_b; g.out_ll = a.ll_x1;
+            pro_src = a.ll_att; g.bias = L.attn_out_b; g.out_ll = a.ll_x1; g.out_llb = a.ll_x1b;
             g.res_mode = l == 0 ? (a.x_in ? RES_XIN : RES_EMBED) : RES_LL; g.res_ll = a.ll_x3; g.res_epoch = ep_prev;
             break;
-        case ST_CQ: pro_src = a.ll_x1; g.bias = L.cross_q_b; g.out_ll = a.ll_q; break;
-        case ST_CO: pro_src = a.ll_catt; g.bias = L.cross_out_b; g.out_ll = a.ll_x2; g.res_mode = RES_LL; g.res_ll = a.ll_x1; break;
-        case ST_M1: pro_src = a.ll_x2; g.epi = EPI_LL_GELU_BF16; g.bias = L.mlp1_b; g.out_ll = a.ll_hid; g.ld_out = 4L * d; g.n_valid = 4 * d; break;
-        case ST_M2: pro_src = a.ll_hid; g.bias = L.mlp2_b; g.out_ll = a.ll_x3; g.res_mode = RES_LL; g.res_ll = a.ll_x2; break;
-        default:    pro_src = a.ll_x3; pro_ep = seq * 64u + (uint32_t)M.Ld; g.epi = EPI_LOGITS; g.out_f32 = a.logits; g.ld_out = a.ld_logits; g.n_valid = M.V; break;
+        case ST_CQ: pro_src = a.ll_x1b; g.bias = L.cross_q_b; g.out_ll = a.ll_q; break;
+        case ST_CO: pro_src = a.ll_catt; g.bias = L.cross_out_b; g.out_ll = a.ll_x2; g.out_llb = a.ll_x2b; g.res_mode = RES_LL; g.res_ll = a.ll_x1; break;
+        case ST_M1: pro_src = a.ll_x2b; g.epi = EPI_LL_GELU_BF16; g.bias = L.mlp1_b; g.out_ll = a.ll_hid; g.ld_out = 4L * d; g.n_valid = 4 * d; break;
+        case ST_M2: pro_src = a.ll_hid; g.bias = L.mlp2_b; g.out_ll = a.ll_x3; g.out_llb = a.ll_x3b; g.res_mode = RES_LL; g.res_ll = a.ll_x2; break;
+        default:    pro_src = a.ll_x3b; pro_ep = seq * 64u + (uint32_t)M.Ld; g.epi = EPI_LOGITS; g.out_f32 = a.logits; g.ld_out = a.ld_logits; g.n_valid = M.V; break;
         }
         int u0, u1;
         gemv_range(g.n_tiles, g.vcta, nctas, u0, u1);

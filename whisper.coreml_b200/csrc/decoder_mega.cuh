@@ -29,6 +29,7 @@ struct MegaArgs {
     uint2 *ll_qkv;                      // [8][3d]   fp32   q | k | v of the new token
     uint2 *ll_att, *ll_catt;            // [8][d/2]  bf16x2 self- / cross-attention output
     uint2 *ll_x1, *ll_x2, *ll_x3;       // [8][d]    fp32   residual stream after self-attention / cross-attention / MLP
+    uint2 *ll_x1b, *ll_x2b, *ll_x3b;    // [8][d/2]  bf16x2 the same values for the LayerNorm prologues (half the words to poll)
     uint2 *ll_q;                        // [8][d]    fp32   cross-attention query
     uint2 *ll_cap;                      // [H][7][8][66] fp32 cross-attention partials (max, sum, o[64]) per key split
     uint2 *ll_hid;                      // [8][2d]   bf16x2 MLP hidden activations
