@@ -6,7 +6,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_long, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwhisper_b200.so")
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libwhisper_b200.so")      # B200_LIB: A/B runs against another build
 _lib = None
 
 f32p = POINTER(c_float)
