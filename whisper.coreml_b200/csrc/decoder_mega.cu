@@ -387,20 +387,28 @@ __device__ __forceinline__ void prologue_ln(const MegaSmem& sm, Ring& ring, cons
                     for (int i = 0; i < MG_IPR; ++i) ok = ok & ll_ok(rr[q].w[i], epoch);
                 if (!ok) ll_backoff(spins, 2);
             } while (!ok);
+            // the five rows' sums go through the butterfly together (rows past nb repeat the last row: no branches in the chain)
+            float s1[5], s2[5];
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
-                if (r0 + q < a.nb) {                                   // warp uniform
-                    float2* dst = reinterpret_cast<float2*>(sm.xs + (long)(r0 + q) * sm.ldx + d);
-                    float s1 = 0.f, s2 = 0.f;
+                float2* dst = reinterpret_cast<float2*>(sm.xs + (long)min(r0 + q, a.nb - 1) * sm.ldx + d);
+                s1[q] = 0.f; s2[q] = 0.f;
 #pragma unroll
-                    for (int i = 0; i < MG_IPR; ++i)
-                        if (v[i]) {
-                            const float x = bf16lo((uint32_t)rr[q].w[i]), y = bf16hi((uint32_t)rr[q].w[i]);
-                            dst[cc[i]] = make_float2(x, y);
-                            s1 += x + y; s2 = fmaf(x, x, fmaf(y, y, s2));
-                        }
-                    row_done(r0 + q, s1, s2);
-                }
+                for (int i = 0; i < MG_IPR; ++i)
+                    if (v[i]) {
+                        const float x = bf16lo((uint32_t)rr[q].w[i]), y = bf16hi((uint32_t)rr[q].w[i]);
+                        dst[cc[i]] = make_float2(x, y);
+                        s1[q] += x + y; s2[q] = fmaf(x, x, fmaf(y, y, s2[q]));
+                    }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int q = 0; q < 5; ++q) { s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o); s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], o); }
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    if (r0 + q < a.nb) { part[(warp * 8 + r0 + q) * 2] = s1[q]; part[(warp * 8 + r0 + q) * 2 + 1] = s2[q]; }
             }
         }
     }
@@ -413,13 +421,14 @@ __device__ __forceinline__ void prologue_ln(const MegaSmem& sm, Ring& ring, cons
         const uint32_t gaddr = smem_u32(sm.ring + (size_t)ring.slot * MG_SLOT) + tid * 8;
         lds5(ga, gaddr); lds5(be, gaddr + d * 4);
         const float inv_d = 1.f / d;
-        // rows in groups of four: the staged items and the row statistics of a group are all fetched before any arithmetic
+        // rows in groups of five (one group for beam size 5): the staged items and the row statistics of a group are all fetched
+        // before any arithmetic
 #pragma unroll 1
-        for (int r0 = 0; r0 < a.nb; r0 += 4) {
-            float2 xv[4][MG_IPR];
-            float mean[4], rstd[4];
+        for (int r0 = 0; r0 < a.nb; r0 += 5) {
+            float2 xv[5][MG_IPR];
+            float mean[5], rstd[5];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 5; ++q) {
                 const int r = min(r0 + q, a.nb - 1);                    // (skipping the rows past nb here made ptxas spill)
                 lds5(xv[q], smem_u32(sm.xs + (long)r * sm.ldx + d) + tid * 8);
                 const float2 p0 = *reinterpret_cast<const float2*>(part + r * 2), p1 = *reinterpret_cast<const float2*>(part + (8 + r) * 2);
@@ -428,7 +437,7 @@ __device__ __forceinline__ void prologue_ln(const MegaSmem& sm, Ring& ring, cons
                 rstd[q] = rsqrtf(fmaxf(((p0.y + p1.y) + (p2.y + p3.y)) * inv_d - mean[q] * mean[q], 0.f) + 1e-5f);
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 5; ++q) {
                 if (r0 + q < a.nb) {
                     uint32_t* row = reinterpret_cast<uint32_t*>(sm.xs + (long)(r0 + q) * sm.ldx);
 #pragma unroll
