@@ -176,6 +176,49 @@ __device__ __forceinline__ void ll_read_rows(const uint2* __restrict__ src, uint
     }
 }
 
+// The same for short rows (row_items <= 384: three items per row and thread, the 64-column attention outputs): all the rows of
+// up to five beams in ONE round of loads (15 x 16 bytes in flight per thread) instead of two rows per round.
+struct LL3 { u64 w[3][2]; };
+__device__ __forceinline__ void ll_load2x3(LL3& r, const uint2* p0, const uint2* p1, const uint2* p2) {
+    asm volatile(
+        "ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%6];\n\t"
+        "ld.relaxed.gpu.global.v2.u64 {%2, %3}, [%7];\n\t"
+        "ld.relaxed.gpu.global.v2.u64 {%4, %5}, [%8];"
+        : "=l"(r.w[0][0]), "=l"(r.w[0][1]), "=l"(r.w[1][0]), "=l"(r.w[1][1]), "=l"(r.w[2][0]), "=l"(r.w[2][1])
+        : "l"(p0), "l"(p1), "l"(p2) : "memory");
+}
+template <class F>
+__device__ __forceinline__ void ll_read_rows3(const uint2* __restrict__ src, uint32_t epoch, int n_rows, int row_items, int tid, int where, F f) {
+    bool v[3];
+    long off[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { v[i] = tid + i * MG_CONSUMERS < row_items; off[i] = v[i] ? 2L * (tid + i * MG_CONSUMERS) : 0L; }
+    for (int r0 = 0; r0 < n_rows; r0 += 5) {
+        LL3 r[5];
+        const uint2* p[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) p[q] = src + 2L * min(r0 + q, n_rows - 1) * row_items;
+        unsigned spins = 0;
+        bool ok;
+        do {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) ll_load2x3(r[q], p[q] + off[0], p[q] + off[1], p[q] + off[2]);
+            ok = true;
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) ok = ok & ll_ok(r[q].w[i][0], epoch) & ll_ok(r[q].w[i][1], epoch);
+            if (!ok) ll_backoff(spins, where);
+        } while (!ok);
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+            if (r0 + q < n_rows) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) if (v[i]) f(r0 + q, tid + i * MG_CONSUMERS, (uint32_t)r[q].w[i][0], (uint32_t)r[q].w[i][1]);
+            }
+    }
+}
+
 // The model descriptor lives in constant memory: its pointers are read at every stage.
 __constant__ MegaModel c_model;
 
@@ -331,11 +374,34 @@ __device__ __forceinline__ void prologue_ln(const MegaSmem& sm, Ring& ring, cons
             if (tid < a.nb) stok[tid] = a.tokens[tid * DEC_TOK_LD + pos];
             consumer_sync();
         }
+        if (a.x_in) {                                                      // reference ABI: embedded rows from the caller, one row per round
 #pragma unroll 1
-        for (int b = 0; b < a.nb; ++b) {                                   // one row per round
-            float2 xv[MG_IPR]; uint32_t tv[MG_IPR] = {0u, 0u, 0u, 0u, 0u};
-            const float2* xp = a.x_in ? reinterpret_cast<const float2*>(a.x_in + (long)b * d) : reinterpret_cast<const float2*>(M.pos_emb + (long)pos * d);
-            const uint32_t* tp = reinterpret_cast<const uint32_t*>(M.tok_emb + (long)(a.x_in ? 0 : stok[b]) * d);
+            for (int b = 0; b < a.nb; ++b) {
+                float2 xv[MG_IPR];
+                const float2* xp = reinterpret_cast<const float2*>(a.x_in + (long)b * d);
+                asm volatile(
+                    "ld.global.nc.v2.f32 {%0, %1}, [%10];\n\t"
+                    "ld.global.nc.v2.f32 {%2, %3}, [%11];\n\t"
+                    "ld.global.nc.v2.f32 {%4, %5}, [%12];\n\t"
+                    "ld.global.nc.v2.f32 {%6, %7}, [%13];\n\t"
+                    "ld.global.nc.v2.f32 {%8, %9}, [%14];"
+                    : "=f"(xv[0].x), "=f"(xv[0].y), "=f"(xv[1].x), "=f"(xv[1].y), "=f"(xv[2].x), "=f"(xv[2].y), "=f"(xv[3].x), "=f"(xv[3].y), "=f"(xv[4].x), "=f"(xv[4].y)
+                    : "l"(xp + cc[0]), "l"(xp + cc[1]), "l"(xp + cc[2]), "l"(xp + cc[3]), "l"(xp + cc[4]) : "memory");
+                float2* dst = reinterpret_cast<float2*>(sm.xs + (long)b * sm.ldx + d);
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < MG_IPR; ++i)
+                    if (v[i]) {
+                        dst[cc[i]] = xv[i];
+                        s1 += xv[i].x + xv[i].y; s2 = fmaf(xv[i].x, xv[i].x, fmaf(xv[i].y, xv[i].y, s2));
+                    }
+                row_done(b, s1, s2);
+            }
+        } else {
+            // the position row is shared by the beams (one load), the beams' token rows are fetched five at a time: one round
+            // of loads instead of one per beam (this prologue opens every step: nothing hides its latency)
+            float2 xv[MG_IPR];
+            const float2* xp = reinterpret_cast<const float2*>(M.pos_emb + (long)pos * d);
             asm volatile(
                 "ld.global.nc.v2.f32 {%0, %1}, [%10];\n\t"
                 "ld.global.nc.v2.f32 {%2, %3}, [%11];\n\t"
@@ -344,25 +410,37 @@ __device__ __forceinline__ void prologue_ln(const MegaSmem& sm, Ring& ring, cons
                 "ld.global.nc.v2.f32 {%8, %9}, [%14];"
                 : "=f"(xv[0].x), "=f"(xv[0].y), "=f"(xv[1].x), "=f"(xv[1].y), "=f"(xv[2].x), "=f"(xv[2].y), "=f"(xv[3].x), "=f"(xv[3].y), "=f"(xv[4].x), "=f"(xv[4].y)
                 : "l"(xp + cc[0]), "l"(xp + cc[1]), "l"(xp + cc[2]), "l"(xp + cc[3]), "l"(xp + cc[4]) : "memory");
-            if (!a.x_in)
-                asm volatile(
-                    "ld.global.nc.u32 %0, [%5];\n\t"
-                    "ld.global.nc.u32 %1, [%6];\n\t"
-                    "ld.global.nc.u32 %2, [%7];\n\t"
-                    "ld.global.nc.u32 %3, [%8];\n\t"
-                    "ld.global.nc.u32 %4, [%9];"
-                    : "=r"(tv[0]), "=r"(tv[1]), "=r"(tv[2]), "=r"(tv[3]), "=r"(tv[4])
-                    : "l"(tp + cc[0]), "l"(tp + cc[1]), "l"(tp + cc[2]), "l"(tp + cc[3]), "l"(tp + cc[4]) : "memory");
-            float2* dst = reinterpret_cast<float2*>(sm.xs + (long)b * sm.ldx + d);
-            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+            for (int b0 = 0; b0 < a.nb; b0 += 5) {
+                uint32_t tv[5][MG_IPR];
 #pragma unroll
-            for (int i = 0; i < MG_IPR; ++i)
-                if (v[i]) {
-                    const float x = xv[i].x + bf16lo(tv[i]), y = xv[i].y + bf16hi(tv[i]);
-                    dst[cc[i]] = make_float2(x, y);
-                    s1 += x + y; s2 = fmaf(x, x, fmaf(y, y, s2));
+                for (int q = 0; q < 5; ++q) {
+                    const uint32_t* tp = reinterpret_cast<const uint32_t*>(M.tok_emb + (long)stok[min(b0 + q, a.nb - 1)] * d);
+                    asm volatile(
+                        "ld.global.nc.u32 %0, [%5];\n\t"
+                        "ld.global.nc.u32 %1, [%6];\n\t"
+                        "ld.global.nc.u32 %2, [%7];\n\t"
+                        "ld.global.nc.u32 %3, [%8];\n\t"
+                        "ld.global.nc.u32 %4, [%9];"
+                        : "=r"(tv[q][0]), "=r"(tv[q][1]), "=r"(tv[q][2]), "=r"(tv[q][3]), "=r"(tv[q][4])
+                        : "l"(tp + cc[0]), "l"(tp + cc[1]), "l"(tp + cc[2]), "l"(tp + cc[3]), "l"(tp + cc[4]) : "memory");
                 }
-            row_done(b, s1, s2);
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    if (b0 + q < a.nb) {                                   // warp uniform
+                        float2* dst = reinterpret_cast<float2*>(sm.xs + (long)(b0 + q) * sm.ldx + d);
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < MG_IPR; ++i)
+                            if (v[i]) {
+                                const float x = xv[i].x + bf16lo(tv[q][i]), y = xv[i].y + bf16hi(tv[q][i]);
+                                dst[cc[i]] = make_float2(x, y);
+                                s1 += x + y; s2 = fmaf(x, x, fmaf(y, y, s2));
+                            }
+                        row_done(b0 + q, s1, s2);
+                    }
+                }
+            }
         }
     } else {
         // x_ll holds bf16x2 LL words here (one word = one 2-column item): half the bytes of the fp32 residual words, and all
@@ -462,9 +540,11 @@ __device__ __forceinline__ void prologue_copy(const MegaSmem& sm, const uint2* _
     consumer_sync();
     ll_wait_sentinels(src, epoch, (row_items * 2) << row_shift, sent_stride, sent_all_rows, nb, tid, 13);
     const int sub_mask = (1 << row_shift) - 1;
-    ll_read_rows(src, epoch, n_rows, row_items, tid, 3, [&](int row, int c, uint32_t w0, uint32_t w1) {
+    auto put = [&](int row, int c, uint32_t w0, uint32_t w1) {
         *reinterpret_cast<uint2*>(sm.xs + (long)(row >> row_shift) * sm.ldx + ((row & sub_mask) * row_items + c) * 4) = make_uint2(w0, w1);
-    });
+    };
+    if (row_items <= 3 * MG_CONSUMERS) ll_read_rows3(src, epoch, n_rows, row_items, tid, 3, put);
+    else ll_read_rows(src, epoch, n_rows, row_items, tid, 3, put);
     consumer_sync();
 }
 
