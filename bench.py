@@ -275,7 +275,7 @@ def main():
         out["roofline"] = {"kernel": "decoder_mega_kernel: one persistent launch per decoder1 token step (LN + 7 GEMVs per layer, self / "
                                      "cross attention, vocabulary projection) + the sampling kernel that follows it",
                            "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                           # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_decoder_mega_r1f_ncu_full.csv (t ~ 10)
+                           # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_decoder_mega_r1g_ncu_full.csv (t ~ 10)
                            "traffic": 354.0e6,
                            "peak_source": which, "bytes_per_step": by, "us_per_step": per_step_ms * 1e3, "steps": dec_steps,
                            "lanes": lanes,
