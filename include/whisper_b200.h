@@ -99,6 +99,10 @@ long logMelSpectrogramDev(const float* d_audio, long n_samples, long padding, in
  * log-mel of the whole file; window w reads frames [seeks[w], seeks[w]+3000) zero-padded past
  * `total_frames` (pad_or_trim, whisper/audio.py:65-88).  Results stay on the device per window. */
 void encoderPredictWindows(const float* d_mel, long total_frames, const int* seeks, int n_windows);
+/* Same with the file's content length: frames at or past `content_frames` read as ZEROS, which is what the reference feeds the
+ * encoder for a partial last window - it slices mel[:, seek : seek + min(3000, content_frames - seek)] out of the mel that
+ * carries 30 s of trailing padding and zero-pads the slice (whisper/transcribe.py:143, 286-290). */
+void encoderPredictWindowsContent(const float* d_mel, long total_frames, long content_frames, const int* seeks, int n_windows);
 void crossKVPredictWindows(int n_windows);
 /* Make window w the current one for decoder256Predict/decoder1Predict/b200DecodeWindow. */
 void b200SelectWindow(int w);

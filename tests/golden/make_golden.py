@@ -152,6 +152,25 @@ def mel_goldens():
     np.savez_compressed(os.path.join(OUT, "ref_mel.npz"), **g)
 
 
+def transcribe_goldens():
+    """whisper.transcribe() of the reference on 100 s of noise with the nano_soft weights (its beam-5 output has consecutive
+    timestamp pairs, so the data-dependent seek of transcribe.py:380-388 and the zero-padded partial last window are exercised)."""
+    from oracle import transcribe as otr
+    dims, ckpt, ref = ref_model("nano", 1, 0.03)
+    audio = torch.cat([synth.noise_audio(10 + i, 480000) for i in range(4)])[:1600000]
+    res = whisper.transcribe(ref, audio, beam_size=5, language="en", condition_on_previous_text=False, temperature=0.0,
+                             compression_ratio_threshold=None, logprob_threshold=None, no_speech_threshold=None, sample_len=40, verbose=None)
+    segs = res["segments"]
+    g = dict(seg_seek=np.array([s["seek"] for s in segs], dtype=np.int64), seg_start=np.array([s["start"] for s in segs]),
+             seg_end=np.array([s["end"] for s in segs]), seg_len=np.array([len(s["tokens"]) for s in segs], dtype=np.int64),
+             seg_tokens=np.array([t for s in segs for t in s["tokens"]], dtype=np.int64))
+    orc = om.OracleModel(dims, ckpt)
+    got = otr.transcribe(orc, audio, od.Specials.load(dims.n_vocab), od.Options(sample_len=40, beam_size=5))
+    print("transcribe: reference seeks", sorted(set(g["seg_seek"].tolist())), "oracle seeks", got["seeks"],
+          "tokens equal", [t for s in got["segments"] for t in s["tokens"]] == g["seg_tokens"].tolist())
+    np.savez_compressed(os.path.join(OUT, "ref_transcribe.npz"), **g)
+
+
 def timing_goldens():
     """The reference's own known-answer tests (tests/test_timing.py:22-52, :67-84) run here,
     plus reference outputs on seeded inputs."""
@@ -184,6 +203,7 @@ def timing_goldens():
 if __name__ == "__main__":
     dump_specials()
     timing_goldens()
+    transcribe_goldens()
     mel_goldens()
     for name in sys.argv[1:] or ["nano", "tiny"]:
         model_goldens(name)

@@ -89,3 +89,35 @@ def test_config3_turbo_split_stages():
         assert _agreement(got.tokens, want.tokens) >= 0.99, (beam, got.tokens, want.tokens)
         assert abs(got.sum_logprob - want.sum_logprob) <= 2e-2 * max(1.0, abs(want.sum_logprob)), (got.sum_logprob, want.sum_logprob)
     m.close()
+
+
+def test_transcribe_reference_seek_and_partial_last_window():
+    """transcribe(seek_mode="reference") against the oracle's restatement of the reference loop (itself pinned to
+    whisper.transcribe() by tests/golden/ref_transcribe.npz): same data-dependent seeks, same tokens; the last window is partial
+    (1024 content frames), so the zero padding of transcribe.py:286-290 is exercised too.  The fixed-window mode is checked on the
+    same clip: its last window (10 s of content) must match the oracle on the zero-padded mel, not on the padded file's mel."""
+    from oracle import transcribe as otr
+    from whisper_b200.transcribe import transcribe
+    dims, ckpt, m = _model("nano", 1, 0.03)
+    orc = om.OracleModel(dims, ckpt)
+    sp = od.Specials.load(dims.n_vocab)
+    audio = torch.cat([synth.noise_audio(10 + i, 480000) for i in range(4)])[:1600000]
+    want = otr.transcribe(orc, audio, sp, od.Options(sample_len=40, beam_size=5))
+    got = transcribe(m, audio, beam_size=5, sample_len=40, seek_mode="reference")
+    assert got["seeks"] == want["seeks"], (got["seeks"], want["seeks"])
+    a = [t for s in got["segments"] for t in s["tokens"]]
+    b = [t for s in want["segments"] for t in s["tokens"]]
+    assert _agreement(a, b) >= 0.99, (a, b)
+    assert [s["seek"] for s in got["segments"]] == [s["seek"] for s in want["segments"]]
+    # fixed windows: 0, 3000, 6000, 9000 (the last one holds 1000 content frames)
+    fixed = transcribe(m, audio, beam_size=5, sample_len=40)
+    assert fixed["seeks"] == [0, 3000, 6000, 9000]
+    mel = oa.log_mel_spectrogram(audio, dims.n_mels, padding=480000)
+    content = mel.shape[-1] - 3000
+    seg = oa.pad_or_trim(mel[:, 9000:content], 3000).contiguous()
+    last = od.decode_window(orc, seg, sp, od.Options(sample_len=40, beam_size=5))
+    got_last = [t for s in fixed["segments"] if s["seek"] == 9000 for t in s["tokens"]]      # the finished segments: a prefix of the decode
+    assert len(got_last) >= 3 and _agreement(got_last, last.tokens[:len(got_last)]) >= 0.99, (got_last, last.tokens)
+    unpadded = od.decode_window(orc, mel[:, 9000:12000].contiguous(), sp, od.Options(sample_len=40, beam_size=5))
+    assert unpadded.tokens != last.tokens          # the case distinguishes zero padding from the padded file's silence frames
+    m.close()

@@ -38,6 +38,7 @@ SIGNATURES = {
     "logMelSpectrogram": (c_long, [f32p, c_long, c_long, c_int, f32p]),
     "logMelSpectrogramDev": (c_long, [c_void_p, c_long, c_long, c_int, c_void_p]),
     "encoderPredictWindows": (None, [c_void_p, c_long, i32p, c_int]),
+    "encoderPredictWindowsContent": (None, [c_void_p, c_long, c_long, i32p, c_int]),
     "crossKVPredictWindows": (None, [c_int]),
     "b200DecodeWindow": (c_int, [i32p, c_int, c_int, c_int, c_int, c_int, i32p, i32p, f32p, f32p]),
     "b200DecodeWindows": (c_int, [i32p, c_int, i32p, c_int, c_int, c_int, c_int, c_int, i32p, i32p, f32p, f32p, i32p]),

@@ -60,11 +60,11 @@ static GemmParams lin(const bf16* A, int M, int K, const bf16* W, const float* b
     return p;
 }
 
-void run_encoder(const float* d_mel, long total_frames, int W) {
+void run_encoder(const float* d_mel, long total_frames, long valid_frames, int W) {
     State& s = S();
     const int d = s.d, M = W * N_AUDIO_CTX;
     cudaStream_t st = s.stream;
-    mel_to_rows(d_mel, total_frames, s.d_seeks, W, s.n_mels, s.cpad, s.melrows, st);
+    mel_to_rows(d_mel, total_frames, valid_frames, s.d_seeks, W, s.n_mels, s.cpad, s.melrows, st);
     {   // conv1 (k3, p1) + GELU: three accumulating passes over row-shifted views (encoder.py:124)
         GemmParams p{};
         for (int k = 0; k < 3; ++k) p.A[k] = s.melrows + (size_t)k * s.cpad;
@@ -440,7 +440,7 @@ void encoderPredict(float* melSegment) {
     use_device();
     B200_CHECK(cudaMemcpyAsync(s.mel_stage, melSegment, (size_t)s.n_mels * N_FRAMES * sizeof(float), cudaMemcpyHostToDevice, s.stream));
     B200_CHECK(cudaMemsetAsync(s.d_seeks, 0, sizeof(int), s.stream));
-    run_encoder(s.mel_stage, N_FRAMES, 1);
+    run_encoder(s.mel_stage, N_FRAMES, N_FRAMES, 1);
     s.cur_window = 0;
     B200_CHECK(cudaStreamSynchronize(s.stream));
 }

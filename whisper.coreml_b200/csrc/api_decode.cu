@@ -178,6 +178,10 @@ void b200SetDecodeSpec(int sot, int eot, int no_timestamps, int timestamp_begin,
 }
 
 void encoderPredictWindows(const float* d_mel, long total_frames, const int* seeks, int n_windows) {
+    encoderPredictWindowsContent(d_mel, total_frames, total_frames, seeks, n_windows);
+}
+
+void encoderPredictWindowsContent(const float* d_mel, long total_frames, long content_frames, const int* seeks, int n_windows) {
     State& s = S();
     if (!s.enc_loaded) { record_error("encoderPredictWindows: encoder not loaded"); return; }
     if (n_windows < 1) return;
@@ -187,7 +191,7 @@ void encoderPredictWindows(const float* d_mel, long total_frames, const int* see
     B200_CHECK(cudaMemcpyAsync(s.d_seeks, seeks, (size_t)n_windows * sizeof(int), cudaMemcpyHostToDevice, s.stream));
     {
         StageTimer t(ST_ENCODER);
-        run_encoder(d_mel, total_frames, n_windows);
+        run_encoder(d_mel, total_frames, content_frames, n_windows);
     }
     s.cur_window = 0;
     B200_CHECK(cudaStreamSynchronize(s.stream));

@@ -60,7 +60,9 @@ void layernorm(const float* x, const float* gamma, const float* beta, float eps,
 // ---------------------------------------------------------------------------------------------------
 // mel (channel-major fp32) -> zero-framed time-major bf16 rows; 32x32 smem transpose.
 // ---------------------------------------------------------------------------------------------------
-__global__ void mel_to_rows_kernel(const float* __restrict__ mel, long total_frames, const int* __restrict__ seeks,
+// Frames at or past `valid_frames` (the file's content, whisper/transcribe.py:286-290: the window is sliced to the content and
+// pad_or_trim ZERO-pads it) and past total_frames read as zeros.
+__global__ void mel_to_rows_kernel(const float* __restrict__ mel, long total_frames, long valid_frames, const int* __restrict__ seeks,
                                    int n_mels, int c_pad, bf16* __restrict__ out) {
     __shared__ float tile[32][33];
     const int w = blockIdx.z;
@@ -70,7 +72,7 @@ __global__ void mel_to_rows_kernel(const float* __restrict__ mel, long total_fra
         const int c = c0 + i;
         const long f = seek + t0 + threadIdx.x;
         float v = 0.f;
-        if (c < n_mels && t0 + threadIdx.x < 3000 && f < total_frames) v = mel[(long)c * total_frames + f];
+        if (c < n_mels && t0 + threadIdx.x < 3000 && f < valid_frames) v = mel[(long)c * total_frames + f];
         tile[i][threadIdx.x] = v;
     }
     __syncthreads();
@@ -87,10 +89,10 @@ __global__ void mel_to_rows_kernel(const float* __restrict__ mel, long total_fra
     }
 }
 
-void mel_to_rows(const float* mel, long total_frames, const int* d_seeks, int n_windows, int n_mels, int c_pad, bf16* out,
+void mel_to_rows(const float* mel, long total_frames, long valid_frames, const int* d_seeks, int n_windows, int n_mels, int c_pad, bf16* out,
                  cudaStream_t s) {
     dim3 grid(cdiv(3000, 32), cdiv(c_pad, 32), n_windows), block(32, 8);
-    mel_to_rows_kernel<<<grid, block, 0, s>>>(mel, total_frames, d_seeks, n_mels, c_pad, out);
+    mel_to_rows_kernel<<<grid, block, 0, s>>>(mel, total_frames, valid_frames < total_frames ? valid_frames : total_frames, d_seeks, n_mels, c_pad, out);
     B200_LAUNCH_CHECK();
 }
 

@@ -9,7 +9,7 @@ void layernorm(const float* x, const float* gamma, const float* beta, float eps,
                int d, cudaStream_t s);
 // log-mel (n_mels, total_frames) fp32 -> time-major, zero-framed bf16 rows for the conv stem:
 // out[(w*3002 + 1 + t), c] = mel[c, seeks[w] + t] (0 beyond total_frames), c < c_pad; rows 0 and 3001 are zero.
-void mel_to_rows(const float* mel, long total_frames, const int* d_seeks, int n_windows, int n_mels, int c_pad,
+void mel_to_rows(const float* mel, long total_frames, long valid_frames, const int* d_seeks, int n_windows, int n_mels, int c_pad,
                  bf16* out, cudaStream_t s);
 void f32_to_bf16(const float* in, bf16* out, long n, cudaStream_t s);
 void bf16_to_f32(const bf16* in, float* out, long n, cudaStream_t s);

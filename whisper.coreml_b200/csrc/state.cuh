@@ -119,7 +119,7 @@ void stage_times(float* out_ms, bool reset);
 
 // sub-model bodies (api.cu)
 bool ensure_encoder_capacity(int n_windows);
-void run_encoder(const float* d_mel, long total_frames, int n_windows);   // seeks already in S().d_seeks
+void run_encoder(const float* d_mel, long total_frames, long valid_frames, int n_windows);   // seeks already in S().d_seeks
 void run_cross_kv(int n_windows);
 void run_prefill(int beam_idx, bool want_chw, int rows);                            // px/pmask -> pout (+ pchw), KV rows -> slot
 // sx -> slogits; d_t / d_skip: optional device-side text_offset and no-op flag (device-driven decode loop)

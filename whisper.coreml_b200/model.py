@@ -151,14 +151,17 @@ class WhisperB200:
     # ---- device-resident fast path --------------------------------------------------------------------------
     current_window = 0
 
-    def encode_windows(self, mel: torch.Tensor, seeks: Sequence[int]) -> int:
-        """Batched encoder + crossKV over independent windows of a device-resident log-mel (n_mels, frames)."""
+    def encode_windows(self, mel: torch.Tensor, seeks: Sequence[int], content_frames: Optional[int] = None) -> int:
+        """Batched encoder + crossKV over independent windows of a device-resident log-mel (n_mels, frames).  Frames at or past
+        `content_frames` are fed as zeros (the reference's pad_or_trim of a partial last window, transcribe.py:286-290)."""
         self.load()
         if not mel.is_cuda:
             mel = mel.to(f"cuda:{self.device_index}")
         mel = mel.to(torch.float32).contiguous()
         arr = np.array(list(seeks), dtype=np.int32)
-        self.lib.encoderPredictWindows(ctypes.c_void_p(mel.data_ptr()), mel.shape[1], arr.ctypes.data_as(_lib.i32p), len(arr))
+        self.lib.encoderPredictWindowsContent(ctypes.c_void_p(mel.data_ptr()), mel.shape[1],
+                                              mel.shape[1] if content_frames is None else int(content_frames),
+                                              arr.ctypes.data_as(_lib.i32p), len(arr))
         self.lib.crossKVPredictWindows(len(arr))
         _lib.check_errors("encode_windows")
         self.n_windows = len(arr)

@@ -1,9 +1,13 @@
 """transcribe(): counterpart of whisper/transcribe.py:41-524 for the configuration the B200 hot path
-targets - fixed 30-s windows, condition_on_previous_text=False, temperature 0 - which makes every window
-independent, so windows can be encoded in batches and sharded over GPUs (`rank::world_size`) with no
-collective in the loop.  The reference's data-dependent seek advance (transcribe.py:380-388, 423-426),
-temperature fallback (:188-228) and prompt carry-over (:300-305) are the part of transcribe() that is
-NOT reproduced; segment slicing by timestamp tokens (:350-410) and word timestamps (:412-421) are."""
+targets - condition_on_previous_text=False, temperature 0.
+
+seek_mode="fixed" (default): fixed 30-s windows, which makes every window independent, so windows are encoded in batches,
+decoded concurrently (decode lanes) and sharded over GPUs (`rank::world_size`) with no collective in the loop.
+seek_mode="reference": the reference's data-dependent seek (transcribe.py:380-388: a window that ends in an unfinished segment
+makes the next window start at its last timestamp) - windows become sequential, one GPU; same segments as whisper.transcribe().
+Segment slicing by timestamp tokens (:350-410), the zero-padded partial last window (:286-290) and word timestamps (:412-421)
+are reproduced in both modes; temperature fallback (:188-228), prompt carry-over (:300-305) and the word-timestamp seek
+adjustments (:423-470) are not."""
 from __future__ import annotations
 
 from typing import List, Optional
@@ -50,7 +54,8 @@ def _segments_from_tokens(tokens: List[int], result: DecodingResult, time_offset
 
 def transcribe(model, audio: torch.Tensor, *, beam_size: Optional[int] = 5, word_timestamps: bool = False,
                sample_len: Optional[int] = None, without_timestamps: bool = False, length_penalty: Optional[float] = None,
-               window_batch: int = 8, rank: int = 0, world_size: int = 1, tokenizer=None, verbose: bool = False) -> dict:
+               window_batch: int = 8, rank: int = 0, world_size: int = 1, tokenizer=None, verbose: bool = False,
+               seek_mode: str = "fixed") -> dict:
     """audio: 1-D 16 kHz float waveform (CPU or CUDA).  Returns {"segments": [...], "windows": n, "language": "en"};
     with a tokenizer (the reference's) segments also carry "text".  Rank r of world_size handles windows r::world_size."""
     model.load()
@@ -65,42 +70,71 @@ def transcribe(model, audio: torch.Tensor, *, beam_size: Optional[int] = 5, word
                            length_penalty=length_penalty)
     segments: List[dict] = []
     decode_steps: List[int] = []
-    for b0 in range(0, len(mine), window_batch):
+
+    def finish_window(result, seek):
+        """segments (+ word timestamps, text) of one decoded window; the window's cross K/V must be selected"""
+        decode_steps.append(result.steps)
+        segment_size = min(N_FRAMES, content_frames - seek)
+        time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
+        if not result.tokens:
+            return []
+        cur = _segments_from_tokens(result.tokens, result, time_offset, segment_size * HOP_LENGTH / SAMPLE_RATE, seek,
+                                    sp.timestamp_begin, sp.eot)
+        if word_timestamps:
+            per_seg = [[t for t in s["tokens"] if t < sp.eot] for s in cur]            # timing.py:283-287
+            text_tokens = [t for seg in per_seg for t in seg]
+            al = align_tokens(sp.sot_sequence, sp.no_timestamps, sp.eot, text_tokens, segment_size)
+            pos = 0
+            for s, toks in zip(cur, per_seg):
+                words = []
+                for k in range(len(toks)):
+                    if al is None:
+                        break
+                    words.append({"token": toks[k], "start": round(time_offset + float(al.jump_times[pos + k]), 2),
+                                  "end": round(time_offset + float(al.jump_times[pos + k + 1]), 2),
+                                  "probability": float(al.text_token_probs[pos + k])})
+                pos += len(toks)
+                s["words"] = words
+        if tokenizer is not None:
+            for s in cur:
+                s["text"] = tokenizer.decode([t for t in s["tokens"] if t < sp.eot])
+        if verbose:
+            for s in cur:
+                print(f"[{s['start']:.2f} --> {s['end']:.2f}] {len(s['tokens'])} tokens")
+        return cur
+
+    if seek_mode == "reference":
+        if world_size != 1:
+            raise ValueError("seek_mode='reference' makes the windows sequential: it cannot be sharded")
+        mine, seek = [], 0
+        while seek < content_frames:                                      # transcribe.py:277-298 (one clip)
+            segment_size = min(N_FRAMES, content_frames - seek)
+            if segment_size * HOP_LENGTH / SAMPLE_RATE < 1.0:
+                break
+            model.encode_windows(mel, [seek], content_frames)
+            result = decode_windows(model, opts, [0])[0]
+            model.select_window(0)
+            mine.append(seek)
+            segments.extend(finish_window(result, seek))
+            t = np.array(result.tokens, dtype=np.int64)
+            is_ts = t >= sp.timestamp_begin
+            consecutive = (np.where(is_ts[:-1] & is_ts[1:])[0] + 1).tolist() if len(t) > 1 else []
+            if consecutive and is_ts[-2:].tolist() != [False, True]:      # unfinished last segment: seek to the last timestamp (:383-388)
+                advance = int(t[consecutive[-1] - 1] - sp.timestamp_begin) * (N_FRAMES // dims.n_audio_ctx)
+            else:
+                advance = segment_size                                    # :380-382, :409
+            if advance <= 0:                                              # the reference would loop forever here
+                break
+            seek += advance
+    elif seek_mode != "fixed":
+        raise ValueError(f"seek_mode {seek_mode!r}: 'fixed' or 'reference'")
+    for b0 in range(0, len(mine) if seek_mode == "fixed" else 0, window_batch):
         batch = mine[b0:b0 + window_batch]
-        model.encode_windows(mel, batch)
+        model.encode_windows(mel, batch, content_frames)
         results = decode_windows(model, opts, range(len(batch)))          # independent windows decode concurrently on the device
         for w, seek in enumerate(batch):
-            result = results[w]
-            model.select_window(w)                                        # word timestamps below read this window's cross K/V
-            decode_steps.append(result.steps)
-            segment_size = min(N_FRAMES, content_frames - seek)
-            time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
-            if not result.tokens:
-                continue
-            cur = _segments_from_tokens(result.tokens, result, time_offset, segment_size * HOP_LENGTH / SAMPLE_RATE, seek,
-                                        sp.timestamp_begin, sp.eot)
-            if word_timestamps:
-                per_seg = [[t for t in s["tokens"] if t < sp.eot] for s in cur]            # timing.py:283-287
-                text_tokens = [t for seg in per_seg for t in seg]
-                al = align_tokens(sp.sot_sequence, sp.no_timestamps, sp.eot, text_tokens, segment_size)
-                pos = 0
-                for s, toks in zip(cur, per_seg):
-                    words = []
-                    for k in range(len(toks)):
-                        if al is None:
-                            break
-                        words.append({"token": toks[k], "start": round(time_offset + float(al.jump_times[pos + k]), 2),
-                                      "end": round(time_offset + float(al.jump_times[pos + k + 1]), 2),
-                                      "probability": float(al.text_token_probs[pos + k])})
-                    pos += len(toks)
-                    s["words"] = words
-            if tokenizer is not None:
-                for s in cur:
-                    s["text"] = tokenizer.decode([t for t in s["tokens"] if t < sp.eot])
-            if verbose:
-                for s in cur:
-                    print(f"[{s['start']:.2f} --> {s['end']:.2f}] {len(s['tokens'])} tokens")
-            segments.extend(cur)
+            model.select_window(w)                                        # word timestamps read this window's cross K/V
+            segments.extend(finish_window(results[w], seek))
     for i, s in enumerate(segments):
         s["id"] = i
     out = {"segments": segments, "windows": len(mine), "seeks": mine, "language": "en",
