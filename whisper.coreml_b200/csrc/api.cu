@@ -510,6 +510,7 @@ void closeDecoder256() {
     dev_free(&s.py); dev_free(&s.pqkv); dev_free(&s.patt); dev_free(&s.phid); dev_free(&s.pq); dev_free(&s.d_dump_slot);
     release_decoder_weights();
     if (s.mega_model) { cudaFree(s.mega_model); s.mega_model = nullptr; }
+    s.align_heads.clear();             // a model loaded next starts from the default alignment heads (model.py:55-58), not this one's
     s.dec256_loaded = false;
     gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
 }
