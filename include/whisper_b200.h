@@ -94,6 +94,13 @@ long logMelSpectrogram(const float* audio, long n_samples, long padding, int n_m
 /* Same, device pointers; the result may stay on the GPU to feed encoderPredictWindows. */
 long logMelSpectrogramDev(const float* d_audio, long n_samples, long padding, int n_mels, float* d_out_mel);
 
+/* Audio ingest on the device (the step in front of log_mel_spectrogram; the reference shells out to ffmpeg, whisper/audio.py:45-62).
+ * b200Pcm16ToMonoDev: interleaved int16 PCM (DEVICE) -> mono fp32 in [-1, 1) (channels averaged, / 32768 as audio.py:62).
+ * b200ResampleDev: rational resampling of a DEVICE fp32 waveform to 16 kHz with the Kaiser(5.0) windowed-sinc polyphase design of
+ * scipy.signal.resample_poly; d_out == NULL returns the output length ceil(n_in * 16000 / sr_in) without computing. */
+long b200Pcm16ToMonoDev(const short* d_pcm, long n_frames, int channels, float* d_out);
+long b200ResampleDev(const float* d_in, long n_in, int sr_in, float* d_out, long out_capacity);
+
 /* Batched encoder + crossKV over `n_windows` independent 30-s windows (the reference loops
  * windows in Python, whisper/transcribe.py:276-306).  d_mel: DEVICE (n_mels, total_frames) fp32
  * log-mel of the whole file; window w reads frames [seeks[w], seeks[w]+3000) zero-padded past

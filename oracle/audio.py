@@ -83,3 +83,30 @@ def pad_or_trim(x: torch.Tensor, length: int = N_FRAMES) -> torch.Tensor:
     if x.shape[-1] < length:
         x = F.pad(x, (0, length - x.shape[-1]))
     return x
+
+
+def resample_poly(x: np.ndarray, sr_in: int, sr_out: int = 16000) -> np.ndarray:
+    """The polyphase resampler of csrc/resample.cu restated in numpy (fp64): Kaiser(5.0) windowed sinc, cut-off 1 / max(up, down),
+    half length 10 * max(up, down), unit DC gain times `up` - the design of scipy.signal.resample_poly, against which
+    tests/test_oracle_golden.py checks this function.  (The reference itself resamples inside an ffmpeg subprocess,
+    whisper/audio.py:45-62; ffmpeg is not in /root/reference and not in this image: parity against it is unpinned.)"""
+    import math
+    g = math.gcd(int(sr_in), int(sr_out))
+    up, down = sr_out // g, sr_in // g
+    x = np.asarray(x, dtype=np.float64)
+    if up == down:
+        return x.copy()
+    max_rate = max(up, down)
+    half = 10 * max_rate
+    m = np.arange(-half, half + 1, dtype=np.float64)
+    h = (1.0 / max_rate) * np.sinc(m / max_rate) * np.i0(5.0 * np.sqrt(np.clip(1 - (m / half) ** 2, 0, 1))) / np.i0(5.0)
+    h = h / h.sum() * up
+    n_out = -(-len(x) * up // down)
+    # y[n] = sum_k x[k] h[n down - k up + half] over |n down - k up| <= half: gather the <= 2 half / up + 1 taps of every output
+    n = np.arange(n_out, dtype=np.int64)[:, None]
+    t = n * down
+    k_first = -((half - t) // up)                        # ceil((t - half) / up)
+    k = k_first + np.arange(2 * half // up + 1, dtype=np.int64)[None, :]
+    j = t - k * up + half
+    ok = (k >= 0) & (k < len(x)) & (j >= 0) & (j <= 2 * half)
+    return (np.where(ok, x[np.clip(k, 0, len(x) - 1)], 0.0) * np.where(ok, h[np.clip(j, 0, 2 * half)], 0.0)).sum(axis=1)

@@ -36,3 +36,30 @@ def test_mel_device_pointer_path_and_edges():
     silence = torch.zeros(16000)
     z = log_mel_spectrogram(silence, 80)
     assert torch.allclose(z, oa.log_mel_spectrogram(silence, 80))
+
+
+@pytest.mark.parametrize("sr", [48000, 44100, 22050, 8000, 16000])
+def test_resample_to_16k_matches_oracle(sr):
+    """csrc/resample.cu against the numpy restatement (fp64) of the same polyphase design: fp32 taps and accumulation."""
+    from whisper_b200.audio import resample_to_16k
+    x = torch.from_numpy(np.random.default_rng(sr).standard_normal(sr * 3 + 17).astype(np.float32)) * 0.1
+    want = oa.resample_poly(x.double().numpy(), sr)
+    got = resample_to_16k(x.cuda(), sr).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < 2e-6
+
+
+def test_load_audio_wav_stereo_44k(tmp_path):
+    """load_audio(): 16-bit PCM WAV -> mono fp32 / 32768 (whisper/audio.py:62) -> 16 kHz, all on the device."""
+    import wave
+    from whisper_b200.audio import load_audio
+    rng = np.random.default_rng(5)
+    pcm = (rng.standard_normal((44100, 2)) * 3000).astype("<i2")
+    path = str(tmp_path / "a.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(44100); w.writeframes(pcm.tobytes())
+    got = load_audio(path).cpu().numpy()
+    mono = pcm.astype(np.float64).mean(axis=1) / 32768.0
+    want = oa.resample_poly(mono, 44100)
+    assert got.shape == want.shape == (16000,)
+    assert np.abs(got - want).max() < 2e-6

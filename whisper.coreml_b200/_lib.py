@@ -37,6 +37,8 @@ SIGNATURES = {
     "b200SetDecodeSpec": (None, [c_int, c_int, c_int, c_int, c_int, i32p, c_int, i32p, c_int]),
     "logMelSpectrogram": (c_long, [f32p, c_long, c_long, c_int, f32p]),
     "logMelSpectrogramDev": (c_long, [c_void_p, c_long, c_long, c_int, c_void_p]),
+    "b200Pcm16ToMonoDev": (c_long, [c_void_p, c_long, c_int, c_void_p]),
+    "b200ResampleDev": (c_long, [c_void_p, c_long, c_int, c_void_p, c_long]),
     "encoderPredictWindows": (None, [c_void_p, c_long, i32p, c_int]),
     "encoderPredictWindowsContent": (None, [c_void_p, c_long, c_long, i32p, c_int]),
     "crossKVPredictWindows": (None, [c_int]),

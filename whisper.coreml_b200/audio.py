@@ -1,6 +1,6 @@
-"""Audio front-end on the device: the counterpart of whisper/audio.py:65-157 (log_mel_spectrogram,
-pad_or_trim).  ffmpeg decoding (audio.py:45-62) is outside the hot path: callers pass a 16 kHz mono
-float waveform."""
+"""Audio front-end on the device: the counterpart of whisper/audio.py:45-157 (load_audio, log_mel_spectrogram, pad_or_trim).
+load_audio here reads PCM WAV files with the standard library and down-mixes / resamples on the GPU (the reference pipes any
+container through an ffmpeg subprocess, audio.py:45-62; other containers are out of scope - pass a waveform instead)."""
 from __future__ import annotations
 
 import ctypes
@@ -52,3 +52,38 @@ def pad_or_trim(array: torch.Tensor, length: int = N_FRAMES, *, axis: int = -1) 
         pad_widths[axis] = (0, length - array.shape[axis])
         array = torch.nn.functional.pad(array, [p for sizes in pad_widths[::-1] for p in sizes])
     return array
+
+
+def resample_to_16k(audio: torch.Tensor, sample_rate: int) -> torch.Tensor:
+    """Rational resampling of a 1-D CUDA waveform to 16 kHz on the device (csrc/resample.cu; the polyphase design of
+    scipy.signal.resample_poly)."""
+    lib = _lib.load()
+    audio = audio.to(torch.float32).contiguous()
+    if not audio.is_cuda:
+        raise ValueError("resample_to_16k expects a CUDA tensor")
+    n_out = lib.b200ResampleDev(None, audio.numel(), int(sample_rate), None, 0)
+    out = torch.empty(n_out, dtype=torch.float32, device=audio.device)
+    got = lib.b200ResampleDev(ctypes.c_void_p(audio.data_ptr()), audio.numel(), int(sample_rate), ctypes.c_void_p(out.data_ptr()), n_out)
+    _lib.check_errors("b200ResampleDev")
+    if got != n_out:
+        raise RuntimeError(f"b200ResampleDev wrote {got} samples, expected {n_out}")
+    return out
+
+
+def load_audio(path: str, sr: int = SAMPLE_RATE, device: str = "cuda") -> torch.Tensor:
+    """whisper/audio.py:25-62 for 16-bit PCM WAV files: mono fp32 waveform at 16 kHz, on the device."""
+    import wave
+
+    import numpy as np
+    if sr != SAMPLE_RATE:
+        raise ValueError("the hot path runs at 16 kHz")
+    with wave.open(path, "rb") as w:
+        if w.getsampwidth() != 2 or w.getcomptype() != "NONE":
+            raise ValueError(f"{path}: only 16-bit PCM WAV is decoded here (got sample width {w.getsampwidth()}, {w.getcomptype()})")
+        channels, rate, n = w.getnchannels(), w.getframerate(), w.getnframes()
+        pcm = torch.from_numpy(np.frombuffer(w.readframes(n), dtype="<i2").copy()).to(device)
+    lib = _lib.load()
+    mono = torch.empty(pcm.numel() // channels, dtype=torch.float32, device=pcm.device)
+    lib.b200Pcm16ToMonoDev(ctypes.c_void_p(pcm.data_ptr()), mono.numel(), channels, ctypes.c_void_p(mono.data_ptr()))
+    _lib.check_errors("b200Pcm16ToMonoDev")
+    return mono if rate == SAMPLE_RATE else resample_to_16k(mono, rate)
