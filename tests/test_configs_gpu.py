@@ -121,3 +121,32 @@ def test_transcribe_reference_seek_and_partial_last_window():
     unpadded = od.decode_window(orc, mel[:, 9000:12000].contiguous(), sp, od.Options(sample_len=40, beam_size=5))
     assert unpadded.tokens != last.tokens          # the case distinguishes zero padding from the padded file's silence frames
     m.close()
+
+
+@pytest.mark.parametrize("tile", [1, 3])
+def test_encoder_parity_with_forced_gemm_tiles(tile):
+    """The whole encoder + crossKV (conv stem with its three row-shifted A maps and window batches, residual epilogues, second
+    fragment-major output) through the 128x128 and the CTA-pair (cta_group::2, 256x256) GEMM kernels - the automatic dispatch only
+    picks the pair kernel from four windows of a large model up, which no other test reaches."""
+    import ctypes
+    from whisper_b200 import _lib
+    dims, ckpt, m = _model("tiny")
+    orc = om.OracleModel(dims, ckpt)
+    audio = torch.cat([synth.noise_audio(3, 480000), synth.noise_audio(4, 480000)])
+    mel = oa.log_mel_spectrogram(audio, dims.n_mels, padding=480000)
+    m.lib.b200TestGemmTile(tile)
+    try:
+        m.encode_windows(mel.cuda(), [0, 3000])
+    finally:
+        m.lib.b200TestGemmTile(0)
+    d, Ld, H = dims.n_text_state, dims.n_text_layer, dims.n_text_head
+    for w, seek in enumerate([0, 3000]):
+        xa = torch.empty(1500, d)
+        m.lib.b200TestGetXa(ctypes.cast(xa.data_ptr(), _lib.f32p), w)
+        xa_ref = orc.encode(mel[:, seek:seek + 3000].contiguous())
+        assert rel(xa, xa_ref) < 2e-2, (tile, w, rel(xa, xa_ref))
+        ck = torch.empty(Ld, H, 64, 1500); cv = torch.empty(Ld, H, 1500, 64)
+        m.lib.b200TestGetCrossKV(ctypes.cast(ck.data_ptr(), _lib.f32p), ctypes.cast(cv.data_ptr(), _lib.f32p), w)
+        ck_ref, cv_ref = om.cross_kv(orc.w, dims, xa_ref)
+        assert rel(ck, ck_ref) < 2e-2 and rel(cv, cv_ref) < 2e-2, (tile, w, rel(ck, ck_ref), rel(cv, cv_ref))
+    m.close()

@@ -616,11 +616,13 @@ void gemm_tcgen05(const GemmParams& p, cudaStream_t stream) {
     if (p.K % BLOCK_K != 0) { record_error("gemm_tcgen05: K=%d is not a multiple of 64", p.K); return; }
     if (g_gemm_force < 0) { const char* e = getenv("B200_GEMM_TILE"); g_gemm_force = e ? atoi(e) : 0; }
     // 128x256 single-CTA tiles keep the smem operand read rate under the 128 B/clk port limit; 128x128 when the problem would
-    // not give every SM a tile.  The CTA-pair kernel (256x256, B200_GEMM_TILE=3) is opt-in: on the encoder's shapes
-    // (M = 3000) it measured 1-10 % slower than 128x256, and 3-7 % faster only from M = 12000 up.
+    // not give every SM a tile.  The CTA-pair kernel (256x256) pays from about four windows per batch (M >= 6000: the 8-window
+    // encoder runs 20.15 instead of 21.07 ms with it); on the headline's M = 3000 it measured 1-10 % slower than 128x256.
+    // B200_GEMM_TILE=1/2/3 forces a configuration.
     const long tiles256 = (long)p.batch * cdiv(p.rows_per_batch, BLOCK_M) * cdiv(p.N, 256);
+    const long tiles_pair = (long)p.batch * cdiv(p.rows_per_batch, 256) * cdiv(p.N, 256);
     int sel = g_gemm_force;
-    if (sel == 0) sel = (tiles256 >= 120 && p.N >= 256) ? 2 : 1;
+    if (sel == 0) sel = ((long)p.batch * p.rows_per_batch >= 6000 && tiles_pair >= 148 && p.N >= 256) ? 3 : (tiles256 >= 120 && p.N >= 256) ? 2 : 1;
     if (sel == 3) launch<0, PAIR_STAGES, 1>(p, stream);
     else if (sel == 2) launch<256, 4, 1>(p, stream);
     else launch<128, 6, 1>(p, stream);
