@@ -150,3 +150,24 @@ def test_encoder_parity_with_forced_gemm_tiles(tile):
         ck_ref, cv_ref = om.cross_kv(orc.w, dims, xa_ref)
         assert rel(ck, ck_ref) < 2e-2 and rel(cv, cv_ref) < 2e-2, (tile, w, rel(ck, ck_ref), rel(cv, cv_ref))
     m.close()
+
+
+def test_transcribe_edge_inputs():
+    """Ragged / degenerate inputs through transcribe(): a clip shorter than 1 s yields no window (transcribe.py:295-298), exactly
+    30 s yields one, digital silence decodes like the oracle (the log-mel is then a constant: audio.py:152-156)."""
+    from whisper_b200.transcribe import transcribe
+    dims, ckpt, m = _model("nano", 1, 0.03)
+    orc = om.OracleModel(dims, ckpt)
+    sp = od.Specials.load(dims.n_vocab)
+    for mode in ("fixed", "reference"):
+        short = transcribe(m, synth.noise_audio(7, 8000), beam_size=5, sample_len=12, seek_mode=mode)
+        assert short["windows"] == 0 and short["segments"] == [] and short["seeks"] == []
+        one = transcribe(m, synth.noise_audio(8, 480000), beam_size=5, sample_len=12, seek_mode=mode)
+        assert one["seeks"] == [0] and one["windows"] == 1
+    silence = torch.zeros(480000)
+    got = transcribe(m, silence, beam_size=None, sample_len=12)                    # greedy
+    mel = oa.log_mel_spectrogram(silence, dims.n_mels, padding=480000)
+    want = od.decode_window(orc, oa.pad_or_trim(mel[:, :3000], 3000).contiguous(), sp, od.Options(sample_len=12, beam_size=None))
+    toks = [t for s in got["segments"] for t in s["tokens"]]
+    assert len(toks) >= 1 and _agreement(toks, want.tokens[:len(toks)]) >= 0.99, (toks, want.tokens)
+    m.close()
