@@ -106,3 +106,27 @@ def test_concurrent_windows_match_sequential():
             assert a.steps == b.steps
             assert abs(a.sum_logprob - b.sum_logprob) <= 1e-3 * max(1.0, abs(a.sum_logprob))
     m.close()
+
+
+def test_decode_runs_into_the_context_limit():
+    """sample_len larger than the text context: the loop must stop when the sequence exceeds n_text_ctx = 448 tokens
+    (decoding.py:732), i.e. after 448 - len(sot_sequence) + 1 steps, with the KV cache written up to its last row (447)."""
+    from whisper_b200.decoding import DecodingOptions, decode
+    from whisper_b200.model import ModelDimensions, WhisperB200
+    dims, ckpt, folder = exported("nano", 1, 0.03)
+    m = WhisperB200(ModelDimensions(**dims.as_dict()), folder).load()
+    mel = oa.log_mel_spectrogram(synth.noise_audio(21, 480000), dims.n_mels, padding=480000)[:, :3000].contiguous()
+    m.encode_windows(mel.cuda(), [0])
+    sp = od.Specials.load(dims.n_vocab)
+    orc = om.OracleModel(dims, ckpt)
+    for beam in (None, 5):
+        want = od.decode_window(orc, mel, sp, od.Options(sample_len=1000, beam_size=beam))
+        got = decode(m, DecodingOptions(sample_len=1000, beam_size=beam), window=0)
+        assert got.steps == want.steps, (beam, got.steps, want.steps)
+        assert want.steps <= 448 - len(sp.sot_sequence) + 1
+        n = min(len(got.tokens), len(want.tokens))
+        assert n > 0 and len(got.tokens) == len(want.tokens)
+        # a long random-weight decode may flip a near-tie somewhere: the prefix up to the first difference must be long
+        same = next((i for i in range(n) if got.tokens[i] != want.tokens[i]), n)
+        assert same >= min(n, 64), (beam, same, n)
+    m.close()
