@@ -135,6 +135,13 @@ def cpu_reference(dims, ckpt_path, n_mels, sample_len, beam, cap_steps, audio_se
     cores: one 30-s window, decoder loop capped at `cap_steps`, extrapolated linearly to `sample_len` steps and to the
     clip's `n_windows` windows."""
     from oracle import audio as oa, decoding as od, model as om, synth
+    # all the host cores the process may use (torch's default without OMP_NUM_THREADS): torchrun exports OMP_NUM_THREADS=1,
+    # which would leave the CPU path single-threaded
+    try:
+        logical = len(os.sched_getaffinity(0))
+    except Exception:
+        logical = os.cpu_count() or 1
+    torch.set_num_threads(max(torch.get_num_threads(), logical, 1))
     ckpt = torch.load(ckpt_path)
     orc = om.OracleModel(dims, ckpt)
     audio = synth.noise_audio(1, 480000)
