@@ -37,8 +37,8 @@ def launches():
     tot = sum(a[1] for a in agg.values())
     out = os.path.join(ROOT, "profiles", f"{rnd}_launches_{tag}_summary.csv")
     with open(out, "w") as fh:
-        fh.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 1 --warmup 1 --cpu-baseline 0 --long-clip 0 "
-                 f"--sample-len 24 ({note}; cold-cache serialised times: compare shares)\n")
+        cmd = os.environ.get("B200_LAUNCH_CMD", "python bench.py --steps 1 --warmup 1 --cpu-baseline 0 --long-clip 0 --sample-len 24")
+        fh.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, {cmd} ({note}; cold-cache serialised times: compare shares)\n")
         fh.write("kernel,launches,total_us,avg_us,share_pct\n")
         for n, a in sorted(agg.items(), key=lambda x: -x[1][1]):
             fh.write(f"{n},{a[0]},{a[1]:.1f},{a[1] / a[0]:.2f},{100 * a[1] / tot:.1f}\n")
