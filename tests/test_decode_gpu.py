@@ -88,23 +88,52 @@ def test_alignment(case):
     assert len(al.jump_times) == len(text) + 1              # one start time per matrix row (no_timestamps row + text rows)
 
 
-def test_concurrent_windows_match_sequential():
-    """b200DecodeWindows decodes independent windows on concurrent lanes (each on half of the SMs): same tokens as one by one."""
+def test_batched_windows_match_sequential():
+    """b200DecodeWindows advances every window of a batch in ONE step kernel (windows x beams = the MMA N dimension, the weights
+    streamed once per step): the tokens must be identical to decoding the windows one by one, for 2, 3 and 8 windows per batch,
+    greedy and beam search (8 windows x 5 beams = 40 rows = 5 n-tiles; 3 windows = a ragged second n-tile)."""
     from whisper_b200.decoding import DecodingOptions, decode, decode_windows
     from whisper_b200.model import ModelDimensions, WhisperB200
     dims, ckpt, folder = exported("tiny", 0, 1.0)
     m = WhisperB200(ModelDimensions(**dims.as_dict()), folder).load()
-    audio = torch.cat([synth.noise_audio(1, 480000), synth.noise_audio(2, 480000), synth.noise_audio(3, 480000)])
+    audio = torch.cat([synth.noise_audio(1 + i, 480000) for i in range(8)])
     mel = oa.log_mel_spectrogram(audio, dims.n_mels, padding=480000)
-    m.encode_windows(mel.cuda(), [0, 3000, 6000])
+    m.encode_windows(mel.cuda(), [3000 * i for i in range(8)])
     for beam in (5, None):
         opts = DecodingOptions(sample_len=32, beam_size=beam)
-        one_by_one = [decode(m, opts, window=w) for w in range(3)]
-        together = decode_windows(m, opts, [0, 1, 2])
-        for a, b in zip(one_by_one, together):
-            assert a.tokens == b.tokens, (beam, a.tokens, b.tokens)
-            assert a.steps == b.steps
-            assert abs(a.sum_logprob - b.sum_logprob) <= 1e-3 * max(1.0, abs(a.sum_logprob))
+        one_by_one = [decode(m, opts, window=w) for w in range(8)]
+        assert len({tuple(r.tokens) for r in one_by_one}) > 1           # the windows really differ
+        for group in ([0, 1], [2, 3, 4], list(range(8)), [7, 0, 3]):
+            together = decode_windows(m, opts, group)
+            for w, b in zip(group, together):
+                a = one_by_one[w]
+                assert a.tokens == b.tokens, (beam, group, w, a.tokens, b.tokens)
+                assert a.steps == b.steps
+                assert abs(a.sum_logprob - b.sum_logprob) <= 1e-3 * max(1.0, abs(a.sum_logprob))
+                assert abs(a.no_speech_prob - b.no_speech_prob) <= 1e-5
+    m.close()
+
+
+def test_batched_windows_finish_at_different_steps():
+    """Windows of one batch that finish at different steps (soft weights emit EOT early in some windows): a finished window keeps
+    riding along in the batched step kernel and must neither change nor disturb the others."""
+    from whisper_b200.decoding import DecodingOptions, decode, decode_windows
+    from whisper_b200.model import ModelDimensions, WhisperB200
+    dims, ckpt, folder = exported("nano", 1, 0.03)
+    m = WhisperB200(ModelDimensions(**dims.as_dict()), folder).load()
+    audio = torch.cat([synth.noise_audio(30 + i, 480000) for i in range(6)])
+    mel = oa.log_mel_spectrogram(audio, dims.n_mels, padding=480000)
+    m.encode_windows(mel.cuda(), [3000 * i for i in range(6)])
+    orc = om.OracleModel(dims, ckpt)
+    sp = od.Specials.load(dims.n_vocab)
+    for beam in (None, 5):
+        opts = DecodingOptions(sample_len=60, beam_size=beam)
+        together = decode_windows(m, opts, range(6))
+        for w in range(6):
+            one = decode(m, opts, window=w)
+            assert one.tokens == together[w].tokens and one.steps == together[w].steps, (beam, w, one.tokens, together[w].tokens)
+        want = od.decode_window(orc, mel[:, :3000].contiguous(), sp, od.Options(sample_len=60, beam_size=beam))
+        assert _agreement(together[0].tokens, want.tokens) >= 0.99, (beam, together[0].tokens, want.tokens)
     m.close()
 
 

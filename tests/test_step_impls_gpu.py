@@ -1,5 +1,5 @@
-"""The two decoder1 implementations - persistent kernel (default) and one kernel per stage (B200_STEP_IMPL=v1) -
-must agree with each other and with the oracle; run in subprocesses because the choice is made once per process."""
+"""The decoder1 implementations - the batched persistent kernel (default; 8 or 4 consumer warps) and the one-window persistent
+kernel it replaced (B200_STEP_IMPL=mega) - must agree with each other; run in subprocesses because the choice is made once per process."""
 import os
 import subprocess
 import sys
@@ -30,8 +30,10 @@ print("RESULT" + json.dumps(out))
 ''' % ROOT
 
 
-def _run(impl):
-    env = dict(os.environ, B200_STEP_IMPL=impl)
+def _run(impl, warps="8"):
+    env = dict(os.environ, B200_STEP_WARPS=warps)
+    if impl:
+        env["B200_STEP_IMPL"] = impl
     p = subprocess.run([sys.executable, "-c", SCRIPT], capture_output=True, text=True, env=env, timeout=600)
     assert p.returncode == 0, p.stderr[-3000:]
     import json
@@ -39,8 +41,9 @@ def _run(impl):
     return json.loads(line[6:])
 
 
-def test_persistent_kernel_matches_per_stage_kernels():
-    a, b = _run("mega"), _run("v1")
+@pytest.mark.parametrize("warps", ["8", "4"])
+def test_batched_kernel_matches_one_window_kernel(warps):
+    a, b = _run("", warps), _run("mega")
     assert a.keys() == b.keys()
     for k in a:
         same = sum(x == y for x, y in zip(a[k][0], b[k][0])) / max(len(a[k][0]), len(b[k][0]), 1)

@@ -1,0 +1,22 @@
+#!/bin/bash
+# round 2, first GPU call: batched step kernel correctness + A/B against the one-window kernel + stage timelines
+cd /root/repo
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/r2a_smi.txt
+timeout 1500 python -m pytest tests/test_decode_gpu.py tests/test_abi_parity.py tests/test_step_impls_gpu.py -q -m gpu 2>&1 | tail -40 > gpurun_out/r2a_tests1.txt
+tail -5 gpurun_out/r2a_tests1.txt
+B="python bench.py --steps 3 --warmup 2 --cpu-baseline 0 --long-clip 4"
+for cfg in "" "B200_STEP_WARPS=4" "B200_STEP_IMPL=mega" "B200_BATCH_WINDOWS=4"; do
+  echo "== $cfg" >> gpurun_out/r2a_bench.txt
+  env $cfg timeout 600 $B 2>gpurun_out/r2a_bench_err.txt | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('rtfx',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'dec1 ms',round(d['stage_ms_per_step']['decoder1'],2),'us/winstep',round(d['roofline']['us_per_step'],2),'enc ms',round(d['stage_ms_per_step']['encoder'],2),'d256',round(d['stage_ms_per_step']['decoder256'],2),'samp',round(d['stage_ms_per_step']['sampling'],2),'long',round(d['long_clip']['value'],1),round(d['long_clip']['decoder1_hbm_frac'],3))" >> gpurun_out/r2a_bench.txt 2>&1
+  tail -3 gpurun_out/r2a_bench_err.txt >> gpurun_out/r2a_bench.txt
+done
+cat gpurun_out/r2a_bench.txt
+for w in 1 2 8; do timeout 300 python tools/step_timeline.py turbo $w > gpurun_out/r2a_timeline_w$w.txt 2>&1; done
+B200_STEP_WARPS=4 timeout 300 python tools/step_timeline.py turbo 2 > gpurun_out/r2a_timeline_w2_cw4.txt 2>&1
+tail -3 gpurun_out/r2a_timeline_w2.txt
+timeout 2400 python -m pytest tests/test_turbo_parity_gpu.py tests/test_word_times_gpu.py -q -m gpu 2>&1 | tail -60 > gpurun_out/r2a_tests2.txt
+tail -15 gpurun_out/r2a_tests2.txt

@@ -4,6 +4,7 @@
 
 #include <stdlib.h>
 
+#include "api_batch.cuh"
 #include "decoder_mega.cuh"
 #include "decoder_step.cuh"
 #include "gemm.cuh"
@@ -281,6 +282,12 @@ static void build_mega_model() {
     if (!s.mega_model && cudaMalloc(&s.mega_model, sizeof(MegaModel)) != cudaSuccess) { cudaGetLastError(); s.mega_model = nullptr; return; }
     B200_CHECK(cudaMemcpy(s.mega_model, &m, sizeof(MegaModel), cudaMemcpyHostToDevice));
     mega_set_model(m);
+    static_assert(sizeof(DbLayer) == sizeof(MegaLayer), "same layer descriptor");
+    DbModel b{};
+    b.d = m.d; b.H = m.H; b.Ld = m.Ld; b.V = m.V; b.n_tiles_vocab = m.n_tiles_vocab;
+    b.tok_emb = m.tok_emb; b.tok_emb_frag = m.tok_emb_frag; b.pos_emb = m.pos_emb; b.ln_w = m.ln_w; b.ln_b = m.ln_b;
+    memcpy(b.layers, m.layers, sizeof(DbLayer) * (size_t)s.Ld);
+    batch_set_model(b);
 }
 
 // columns of the bf16 activation rows in shared memory: the MLP hidden row (4d) or the 256 cached K | V rows of a self-attention unit (64 KB)
@@ -506,6 +513,7 @@ void closeDecoder256() {
     use_device();
     B200_CHECK(cudaDeviceSynchronize());
     decode_free_lanes();
+    batch_free();
     dev_free(&s.mkv); dev_free(&s.table); dev_free(&s.px); dev_free(&s.pout); dev_free(&s.pmask); dev_free(&s.pchw);
     dev_free(&s.py); dev_free(&s.pqkv); dev_free(&s.patt); dev_free(&s.phid); dev_free(&s.pq); dev_free(&s.d_dump_slot);
     release_decoder_weights();
@@ -560,6 +568,7 @@ void closeDecoder1() {
     use_device();
     B200_CHECK(cudaDeviceSynchronize());
     decode_free_lanes();
+    batch_free();
     dev_free(&s.sx); dev_free(&s.sqkv); dev_free(&s.sq); dev_free(&s.slogits); dev_free(&s.smask); dev_free(&s.spart);
     dev_free(&s.scounters); dev_free(&s.satt); dev_free(&s.shid);
     dev_free(&s.sxin); dev_free(&s.mega_ll); dev_free(&s.mega_barrier);
@@ -599,7 +608,8 @@ void decoder1Predict(float* x, float* qk_mask, int text_offset, float* out_x) {
     const bool mega = mega_available();
     B200_CHECK(cudaMemcpyAsync(mega ? s.sxin : s.sx, x, nb * d * sizeof(float), cudaMemcpyHostToDevice, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.smask, qk_mask, (size_t)(nb == 1 ? 450 : 449) * sizeof(float), cudaMemcpyHostToDevice, s.stream));
-    if (mega) run_step_mega(nb, text_offset, s.smask, s.sxin, nullptr);
+    if (batch_available()) run_step_batch_abi(nb, text_offset, s.smask, s.sxin);
+    else if (mega) run_step_mega(nb, text_offset, s.smask, s.sxin, nullptr);
     else run_step(nb, text_offset, s.smask, true, nullptr, nullptr);
     B200_CHECK(cudaMemcpyAsync(out_x, s.slogits, (size_t)nb * s.V * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     B200_CHECK(cudaStreamSynchronize(s.stream));

@@ -7,6 +7,7 @@
 #include <tuple>
 #include <vector>
 
+#include "api_batch.cuh"
 #include "decoder_mega.cuh"
 #include "decoder_step.cuh"
 #include "ops.cuh"
@@ -32,6 +33,8 @@ struct DecodeCtx {
     bool ready = false;
 };
 static DecodeCtx g_dc;
+
+DecodeSpec decode_spec() { return g_dc.spec; }
 
 static bool ensure_decode_ctx() {
     DecodeCtx& c = g_dc;
@@ -165,7 +168,16 @@ void b200SetDecodeSpec(int sot, int eot, int no_timestamps, int timestamp_begin,
     State& s = S();
     DecodeCtx& c = g_dc;
     if (!s.V) { record_error("b200SetDecodeSpec: load the decoder first (n_vocab unknown)"); return; }
+    if (eot < 0 || eot >= s.V || timestamp_begin < 0 || timestamp_begin >= s.V) { record_error("b200SetDecodeSpec: eot %d / timestamp_begin %d outside the vocabulary (%d)", eot, timestamp_begin, s.V); return; }
+    if (n_blank > 4) { record_error("b200SetDecodeSpec: %d blank tokens (at most 4 are supported)", n_blank); return; }
+    if ((timestamp_begin + SAMPLE_TEXT_CHUNKS - 1) / SAMPLE_TEXT_CHUNKS > SAMPLE_CHUNK_TOKENS_MAX || s.V - timestamp_begin > SAMPLE_CHUNK_TOKENS_MAX) {
+        record_error("b200SetDecodeSpec: vocabulary chunks of %d text / %d timestamp tokens exceed %d", (timestamp_begin + SAMPLE_TEXT_CHUNKS - 1) / SAMPLE_TEXT_CHUNKS,
+                     s.V - timestamp_begin, SAMPLE_CHUNK_TOKENS_MAX);
+        return;
+    }
     use_device();
+    B200_CHECK(cudaDeviceSynchronize());
+    decode_clear_graphs();                                              // captured step graphs hold the old spec (and d_suppress) by value
     c.spec.sot = sot; c.spec.eot = eot; c.spec.no_timestamps = no_timestamps; c.spec.timestamp_begin = timestamp_begin;
     c.spec.no_speech = no_speech; c.spec.n_vocab = s.V;
     for (int i = 0; i < 4; ++i) c.spec.blank[i] = i < n_blank ? blank[i] : -1;
@@ -418,6 +430,10 @@ int b200DecodeWindows(const int* windows, int n_windows, const int* initial_toke
         if (windows[w] < 0 || windows[w] >= (s.ckv_cap > 0 ? s.ckv_cap : 1)) { record_error("b200DecodeWindows: window %d outside [0, %d)", windows[w], s.ckv_cap); return 0; }
     use_device();
     activate_lane(0);
+    if (c.spec.n_vocab != s.V || c.spec.eot < 0) { record_error("decode: call b200SetDecodeSpec (n_vocab %d) first", s.V); return 0; }
+    if (batch_available())                                              // every window of a batch advances in ONE step kernel
+        return decode_windows_batch(windows, n_windows, initial_tokens, n_initial, beam_size, sample_len, without_timestamps,
+                                    max_initial_timestamp_index, out_tokens, out_lengths, out_sum_logprobs, out_no_speech, out_steps);
     if (!ensure_decode_ctx()) return 0;
     // lanes: only the persistent step kernel can share the GPU between decodes; B200_DECODE_LANES=1 turns the overlap off
     static const int max_lanes = [] { const char* e = getenv("B200_DECODE_LANES"); const int v = e ? atoi(e) : MAX_LANES; return v < 1 ? 1 : (v > MAX_LANES ? MAX_LANES : v); }();

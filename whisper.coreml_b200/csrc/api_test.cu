@@ -1,5 +1,6 @@
 // Test hooks exported through the C ABI (tests/ only; see include/whisper_b200.h).
 #include <algorithm>
+#include "api_batch.cuh"
 #include "decoder_mega.cuh"
 #include "gemm.cuh"
 #include "ops.cuh"
@@ -203,6 +204,7 @@ extern "C" int b200TestAttentionTimeline(const void* dQKV, void* dO, int n_tok, 
 extern "C" int b200TestStepTimeline(int enable, unsigned long long* out, int cap_ctas) {
     State& s = S();
     use_device();
+    if (batch_available()) return batch_timeline(enable, out, cap_ctas);
     mega_available();
     const size_t n = (size_t)s.n_sms * MEGA_DBG_LD;
     if (enable) {

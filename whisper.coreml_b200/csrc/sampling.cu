@@ -51,8 +51,42 @@ void sample_and_update(const SampleArgs& a, const BeamUpdateArgs& u, cudaStream_
     B200_LAUNCH_CHECK();
 }
 
-__global__ void __launch_bounds__(1024) no_speech_kernel(const float* __restrict__ x, int V, int tok, DecodeState* st) {
+// batched windows: blockIdx.z = window; the last CTA of a window to publish its partial updates that window's beams
+__global__ void __launch_bounds__(256) sample_update_batch_kernel(const SampleBatchArgs b) {
+    __shared__ int stage[DEC_MAX_BEAMS * DEC_TOK_LD];
+    __shared__ int s_last;
+    const int w = blockIdx.z;
+    SampleArgs a;
+    a.logits = b.logits + (long)w * b.row_stride_w * b.ld_logits; a.ld_logits = (long)b.row_stride_b * b.ld_logits;
+    a.tokens = b.tokens + (long)w * b.slot_stride * DEC_TOK_LD; a.st = b.st + w; a.spec = b.spec; a.nb = b.nb; a.k = b.k;
+    a.part = b.part + w; a.cand_lp = b.cand_lp + w * DEC_MAX_BEAMS * SAMPLE_MAX_K; a.cand_tok = b.cand_tok + w * DEC_MAX_BEAMS * SAMPLE_MAX_K;
+    sample_partial_body<256>(a, blockIdx.x, blockIdx.y, threadIdx.x, BlockSync());
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned n = gridDim.x * gridDim.y;
+        s_last = atomicAdd(&a.part->arrivals, 1u) == n - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) a.part->arrivals = 0;
+    BeamUpdateArgs u;
+    u.part = a.part; u.timestamp_begin = b.spec.timestamp_begin; u.update = 1; u.cand_lp = a.cand_lp; u.cand_tok = a.cand_tok; u.nb = b.nb; u.k = b.k;
+    u.tokens = b.tokens + (long)w * b.slot_stride * DEC_TOK_LD; u.table = b.table + (long)w * b.slot_stride * 448;
+    u.fin_tokens = b.fin_tokens + (long)w * DEC_MAX_BEAMS * DEC_TOK_LD; u.st = b.st + w; u.eot = b.spec.eot; u.n_text_ctx = b.n_text_ctx;
+    beam_update_body<256, false>(u, stage, nullptr, threadIdx.x, BlockSync());
+}
+
+void sample_and_update_batch(const SampleBatchArgs& a, cudaStream_t s) {
+    dim3 grid(SAMPLE_CHUNKS, a.nb, a.W);
+    sample_update_batch_kernel<<<grid, 256, 0, s>>>(a);
+    B200_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(1024) no_speech_kernel(const float* __restrict__ x, int V, int tok, DecodeState* st, long ld) {
     __shared__ float rm[32], rs[32];
+    x += (long)blockIdx.x * ld; st += blockIdx.x;                      // one window per CTA
     float m = -INFINITY, s = 0.f;
     for (int v = threadIdx.x; v < V; v += 1024) online_add(m, s, x[v]);
 #pragma unroll
@@ -66,8 +100,12 @@ __global__ void __launch_bounds__(1024) no_speech_kernel(const float* __restrict
         if (threadIdx.x == 0) st->no_speech_prob = expf(x[tok] - m) / s;
     }
 }
+void no_speech_prob_batch(const float* logits, long ld_logits, int n_vocab, int no_speech, DecodeState* st, int W, cudaStream_t s) {
+    no_speech_kernel<<<W, 1024, 0, s>>>(logits, n_vocab, no_speech, st, ld_logits);
+    B200_LAUNCH_CHECK();
+}
 void no_speech_prob(const float* logits, int n_vocab, int no_speech, DecodeState* st, cudaStream_t s) {
-    no_speech_kernel<<<1, 1024, 0, s>>>(logits, n_vocab, no_speech, st);
+    no_speech_kernel<<<1, 1024, 0, s>>>(logits, n_vocab, no_speech, st, 0);
     B200_LAUNCH_CHECK();
 }
 

@@ -31,6 +31,7 @@ struct DecodeState {                   // one per decode, in device memory
 // Phase 1: the vocabulary is cut into SAMPLE_TEXT_CHUNKS text chunks + 1 timestamp chunk per beam (one CTA each, so
 // a 5-beam step fills the GPU); each CTA applies the logit filters and leaves (max, sum exp) and its top-k.
 constexpr int SAMPLE_TEXT_CHUNKS = 28, SAMPLE_CHUNKS = SAMPLE_TEXT_CHUNKS + 1, SAMPLE_MAX_K = DEC_MAX_BEAMS + 1;
+constexpr int SAMPLE_CHUNK_TOKENS_MAX = 2048;   // tokens one (chunk, beam) CTA can hold (sampling_dev.cuh: SP_CHUNK_MAX)
 struct SamplePartials {                // device scratch
     float m[DEC_MAX_BEAMS][SAMPLE_CHUNKS], s[DEC_MAX_BEAMS][SAMPLE_CHUNKS];
     float topv[DEC_MAX_BEAMS][SAMPLE_CHUNKS][SAMPLE_MAX_K];
@@ -62,6 +63,21 @@ struct BeamUpdateArgs {
 void beam_update(const BeamUpdateArgs& a, cudaStream_t s);
 // Both phases in ONE launch: the CTA whose partial arrives last runs phase 2 (one kernel boundary less per token step).
 void sample_and_update(const SampleArgs& a, const BeamUpdateArgs& u, cudaStream_t s);
+
+// ---- batched windows: one launch samples and updates every window of a batched decoder step --------------------------------
+// Window w owns rows [w * slot_stride, w * slot_stride + nb) of tokens / table, st[w], part[w], fin_tokens[w], cand_*[w]; the
+// logits of its beam b are row w * row_stride_w + b * row_stride_b (0 for b right after the prompt: all beams share the row).
+struct SampleBatchArgs {
+    const float* logits; long ld_logits; int row_stride_w, row_stride_b;
+    int* tokens; int* table; int* fin_tokens;      // [W * slot_stride][DEC_TOK_LD], [W * slot_stride][448], [W][DEC_MAX_BEAMS][DEC_TOK_LD]
+    DecodeState* st; SamplePartials* part;         // [W]
+    float* cand_lp; int* cand_tok;                 // [W][DEC_MAX_BEAMS * SAMPLE_MAX_K]
+    DecodeSpec spec;
+    int W, nb, k, slot_stride, n_text_ctx;
+};
+void sample_and_update_batch(const SampleBatchArgs& a, cudaStream_t s);
+// st[w].no_speech_prob for W windows from logits rows w
+void no_speech_prob_batch(const float* logits, long ld_logits, int n_vocab, int no_speech, DecodeState* st, int W, cudaStream_t s);
 
 // st->no_speech_prob = softmax(logits)[no_speech]   (whisper/decoding.py:716-720)
 void no_speech_prob(const float* logits, int n_vocab, int no_speech, DecodeState* st, cudaStream_t s);

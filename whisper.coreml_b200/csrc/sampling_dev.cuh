@@ -51,7 +51,7 @@ __device__ __forceinline__ void probe(int idx, int tid) { if (g_probe && tid == 
 __device__ __forceinline__ void probe(int, int) {}
 #endif
 
-constexpr int SP_CHUNK_MAX = 2048;                     // >= largest chunk (1799 text / 1502 timestamp tokens)
+constexpr int SP_CHUNK_MAX = SAMPLE_CHUNK_TOKENS_MAX;                     // >= largest chunk (1799 text / 1502 timestamp tokens)
 
 // One (chunk, beam) unit; `tid` in [0, SP_THREADS); sync() is a barrier over exactly those SP_THREADS threads (256 in the
 // stand-alone kernel, the 128 consumer threads inside the persistent step kernel).
@@ -215,7 +215,7 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
         const int warp = bw;                                 // one warp per beam
         const SamplePartials& P = *a.part;
         float m = -INFINITY, s = 0.f;
-        if (lane < SAMPLE_CHUNKS) { m = P.m[warp][lane]; s = P.s[warp][lane]; }
+        if (lane < SAMPLE_CHUNKS) { m = __ldcg(&P.m[warp][lane]); s = __ldcg(&P.s[warp][lane]); }   // other CTAs' partials: read at L2 (never a stale L1 line)
         float mt = lane < SAMPLE_TEXT_CHUNKS ? m : -INFINITY, stx = lane < SAMPLE_TEXT_CHUNKS ? s : 0.f;   // text group
         float mq = lane == SAMPLE_TEXT_CHUNKS ? m : -INFINITY, sq = lane == SAMPLE_TEXT_CHUNKS ? s : 0.f;  // timestamp group
 #pragma unroll
@@ -236,7 +236,7 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
 #pragma unroll
         for (int e = 0; e < 9; ++e) {
             cv[e] = -INFINITY; ci[e] = 0x7fffffff;
-            if (mine && e < a.k) { cv[e] = P.topv[warp][lane][e]; ci[e] = P.topi[warp][lane][e]; }
+            if (mine && e < a.k) { cv[e] = __ldcg(&P.topv[warp][lane][e]); ci[e] = __ldcg(&P.topi[warp][lane][e]); }
         }
         unsigned taken = 0;
         for (int c = 0; c < a.k; ++c) {
