@@ -100,6 +100,13 @@ long logMelSpectrogramDev(const float* d_audio, long n_samples, long padding, in
  * scipy.signal.resample_poly; d_out == NULL returns the output length ceil(n_in * 16000 / sr_in) without computing. */
 long b200Pcm16ToMonoDev(const short* d_pcm, long n_frames, int channels, float* d_out);
 long b200ResampleDev(const float* d_in, long n_in, int sr_in, float* d_out, long out_capacity);
+/* FLAC container decode on the HOST (the reference leaves every container to ffmpeg, whisper/audio.py:45-62).  b200FlacInfo reads
+ * STREAMINFO (returns 0, or -1 if `data` is not a FLAC stream); md5_16 receives the encoder's MD5 of the decoded PCM, which is what
+ * the parity test checks the decoder against.  b200FlacDecode writes interleaved int32 samples (right-justified, bits_per_sample
+ * significant bits) and returns the samples per channel, or -1. */
+int  b200FlacInfo(const unsigned char* data, long n_bytes, int* sample_rate, int* channels, int* bits_per_sample, long* total_samples,
+                  unsigned char* md5_16);
+long b200FlacDecode(const unsigned char* data, long n_bytes, int* out_interleaved, long cap_samples_per_channel);
 
 /* Batched encoder + crossKV over `n_windows` independent 30-s windows (the reference loops
  * windows in Python, whisper/transcribe.py:276-306).  d_mel: DEVICE (n_mels, total_frames) fp32

@@ -15,7 +15,7 @@ __device__ __forceinline__ uint4 ld16(const uint4* p) {
     return r;
 }
 // MODE 0..3: register loads, B per thread in flight; MODE 4: one cp.async.bulk of the whole buffer into shared memory
-template <int MODE, int B>
+template <int MODE, int B, int ROT = 0>
 __global__ void __launch_bounds__(128, 1) k(const uint4* buf, int n16, int iters, unsigned* out, long long* cyc) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128, 1) k(const uint4* buf, int n16, int iters
             for (int base = 0; base < n16; base += 128 * B) {
                 uint4 r[B];
 #pragma unroll
-                for (int i = 0; i < B; ++i) { const int e = base + i * 128 + tid; if (e < n16) r[i] = ld16<MODE>(buf + e); }
+                for (int i = 0; i < B; ++i) { const int e = base + i * 128 + tid; if (e < n16) r[i] = ld16<MODE>(buf + (ROT ? (e + blockIdx.x * 64) % n16 : e)); }
 #pragma unroll
                 for (int i = 0; i < B; ++i) { const int e = base + i * 128 + tid; if (e < n16) acc += r[i].x ^ r[i].y ^ r[i].z ^ r[i].w; }
             }
@@ -48,10 +48,10 @@ __global__ void __launch_bounds__(128, 1) k(const uint4* buf, int n16, int iters
     out[blockIdx.x * 128 + tid] = acc;
     if (tid == 0) cyc[blockIdx.x] = t1 - t0;
 }
-template <int MODE, int B> void run(const char* name, const uint4* buf, int bytes, unsigned* out, long long* cyc, int n_sms) {
+template <int MODE, int B, int ROT = 0> void run(const char* name, const uint4* buf, int bytes, unsigned* out, long long* cyc, int n_sms) {
     const int iters = 200;
-    cudaFuncSetAttribute(k<MODE, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    k<MODE, B><<<n_sms, 128, 200 * 1024>>>(buf, bytes / 16, iters, out, cyc);
+    cudaFuncSetAttribute(k<MODE, B, ROT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    k<MODE, B, ROT><<<n_sms, 128, 220 * 1024>>>(buf, bytes / 16, iters, out, cyc);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
     long long h[256]; cudaMemcpy(h, cyc, n_sms * 8, cudaMemcpyDeviceToHost);
@@ -62,9 +62,11 @@ template <int MODE, int B> void run(const char* name, const uint4* buf, int byte
 int main() {
     int n_sms = 0; cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, 0);
     uint4* buf; unsigned* out; long long* cyc;
-    cudaMalloc(&buf, 1 << 20); cudaMemset(buf, 1, 1 << 20); cudaMalloc(&out, 1 << 20); cudaMalloc(&cyc, 4096);
-    for (int bytes : {12800, 25600, 51200, 102400}) {
+    cudaMalloc(&buf, 1 << 20); cudaMemset(buf, 1, 1 << 20); cudaFuncSetAttribute(k<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); cudaMalloc(&out, 1 << 20); cudaMalloc(&cyc, 4096);
+    for (int bytes : {12800, 25600, 51200, 102400, 204800}) {
         run<0, 13>("ld.relaxed.gpu.v2.u64 x13", buf, bytes, out, cyc, n_sms);
+        run<0, 13, 1>("ld.relaxed.gpu.v2.u64 x13 rotated", buf, bytes, out, cyc, n_sms);
+        run<0, 4>("ld.relaxed.gpu.v2.u64 x4", buf, bytes, out, cyc, n_sms);
         run<1, 13>("ld.global.cg.v4 x13", buf, bytes, out, cyc, n_sms);
         run<2, 13>("ld.global.nc.v4 x13", buf, bytes, out, cyc, n_sms);
         run<3, 13>("ld.volatile.v4 x13", buf, bytes, out, cyc, n_sms);

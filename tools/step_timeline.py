@@ -45,3 +45,20 @@ for it in range(n_stages):
     prev_done = done
 print("step total", (T[:, :2 * n_stages + 1].max() - t0) / 1000.0, "us")
 print("mean us per stage kind (last done -> last done):", {k: round(float(np.mean(v)), 2) for k, v in per_kind.items()})
+
+probe = os.environ.get("B200_STEP_PROBE")
+if probe is not None:
+    it = int(probe)
+    print(f"inner marks of stage {it}: SM cycles since the CTA's first inner mark, and since the previous mark (median over CTAs; thread 0 only)")
+    cols = [k for k in range(39) if (T[:, 600 + k] > 0).sum() * 2 >= T.shape[0] or (T[:, 600 + k] > 0).sum() >= 20]
+    prev = None
+    for k in cols:
+        ok = (T[:, 600 + k] > 0) & (T[:, 600 + cols[0]] > 0)
+        since0 = np.median(T[ok, 600 + k] - T[ok, 600 + cols[0]])
+        d = ""
+        if prev is not None:
+            ok2 = ok & (T[:, 600 + prev] > 0)
+            d = f"{np.median(T[ok2, 600 + k] - T[ok2, 600 + prev]):8.0f}"
+        print(f"  mark {k:2d}: {since0:9.0f} {d}   ({int(ok.sum())} CTAs)")
+        prev = k
+    print("  poll retries of the last copy batch (thread 0), max over CTAs:", int(T[:, 639].max()))

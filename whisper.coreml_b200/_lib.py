@@ -39,6 +39,8 @@ SIGNATURES = {
     "logMelSpectrogramDev": (c_long, [c_void_p, c_long, c_long, c_int, c_void_p]),
     "b200Pcm16ToMonoDev": (c_long, [c_void_p, c_long, c_int, c_void_p]),
     "b200ResampleDev": (c_long, [c_void_p, c_long, c_int, c_void_p, c_long]),
+    "b200FlacInfo": (c_int, [c_void_p, c_long, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_long), c_void_p]),
+    "b200FlacDecode": (c_long, [c_void_p, c_long, i32p, c_long]),
     "encoderPredictWindows": (None, [c_void_p, c_long, i32p, c_int]),
     "encoderPredictWindowsContent": (None, [c_void_p, c_long, c_long, i32p, c_int]),
     "crossKVPredictWindows": (None, [c_int]),

@@ -40,7 +40,7 @@ static bool g_db_model_set = false;
 
 struct BatchGraph { cudaGraphExec_t exec = nullptr; long launches = 0; };
 static std::map<std::vector<long>, BatchGraph> g_batch_graphs;
-static void batch_clear_graphs() {
+void batch_clear_graphs() {
     for (auto& kv : g_batch_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     g_batch_graphs.clear();
 }
@@ -121,6 +121,7 @@ static bool fill_geometry(DbArgs& a, int rows) {
     return true;
 }
 
+static int probe_stage() { static const int v = getenv("B200_STEP_PROBE") ? atoi(getenv("B200_STEP_PROBE")) : -1; return v; }
 static int grid_ctas() {
     static const int force = getenv("B200_STEP_CTAS") ? atoi(getenv("B200_STEP_CTAS")) : 0;      // experiments: fixed grid size
     return force > 0 ? force : S().n_sms;
@@ -142,7 +143,7 @@ bool run_step_batch_abi(int nb, int text_offset, const float* d_mask, const floa
     if (!fill_geometry(a, nb)) return false;
     db_carve_ll(a, c.abi_ll, s.d, s.H);
     a.logits = s.slogits; a.ld_logits = s.V; a.mkv = s.mkv; a.kv_stride = (long)s.bs * N_TEXT_CTX * s.d; a.table = s.table;
-    a.mask = d_mask; a.x_in = d_x_in; a.text_offset = text_offset; a.barrier = c.abi_barrier; a.dbg = c.dbg;
+    a.mask = d_mask; a.x_in = d_x_in; a.text_offset = text_offset; a.barrier = c.abi_barrier; a.dbg = c.dbg; a.dbg_stage = probe_stage(); a.copy_u = getenv("B200_STEP_COPYU") ? atoi(getenv("B200_STEP_COPYU")) : 13;
     return db_launch(a, grid_ctas(), s.stream);
 }
 
@@ -167,7 +168,7 @@ static DbArgs step_args(const BatchJob& j, bool prompt, int text_offset) {
     fill_geometry(a, a.W * a.nbw);
     db_carve_ll(a, c.ll, s.d, s.H);
     a.logits = c.logits; a.ld_logits = s.V; a.mkv = c.mkv; a.kv_stride = (long)DB_MAX_ROWS * N_TEXT_CTX * s.d; a.table = c.table; a.tokens = c.tokens;
-    a.st = prompt ? nullptr : c.st; a.text_offset = text_offset; a.barrier = c.barrier; a.dbg = c.dbg;
+    a.st = prompt ? nullptr : c.st; a.text_offset = text_offset; a.barrier = c.barrier; a.dbg = c.dbg; a.dbg_stage = probe_stage(); a.copy_u = getenv("B200_STEP_COPYU") ? atoi(getenv("B200_STEP_COPYU")) : 13;
     return a;
 }
 

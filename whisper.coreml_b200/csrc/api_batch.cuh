@@ -7,6 +7,7 @@ namespace b200 {
 
 void batch_set_model(const DbModel& m);       // both decoders loaded: descriptor -> constant memory
 void batch_free();                            // decoder closed
+void batch_clear_graphs();                    // captured step graphs hold the decode spec by value
 bool batch_available();                       // batched step kernel usable for the loaded model (B200_STEP_IMPL unset)?
 int batch_max_windows(int nb);
 bool run_step_batch_abi(int nb, int text_offset, const float* d_mask, const float* d_x_in);

@@ -22,7 +22,7 @@ namespace b200 {
 struct DecodeCtx {
     DecodeSpec spec;
     std::vector<uint8_t> h_suppress;
-    uint8_t* d_suppress = nullptr;
+    uint8_t* d_suppress = nullptr; size_t suppress_cap = 0;
     DecodeState* st = nullptr;          // device
     int* tokens = nullptr;              // [8][449]
     int* fin_tokens = nullptr;          // [8][449]
@@ -177,14 +177,16 @@ void b200SetDecodeSpec(int sot, int eot, int no_timestamps, int timestamp_begin,
     }
     use_device();
     B200_CHECK(cudaDeviceSynchronize());
-    decode_clear_graphs();                                              // captured step graphs hold the old spec (and d_suppress) by value
+    decode_clear_graphs(); batch_clear_graphs();                        // captured step graphs hold the old spec (and d_suppress) by value
     c.spec.sot = sot; c.spec.eot = eot; c.spec.no_timestamps = no_timestamps; c.spec.timestamp_begin = timestamp_begin;
     c.spec.no_speech = no_speech; c.spec.n_vocab = s.V;
     for (int i = 0; i < 4; ++i) c.spec.blank[i] = i < n_blank ? blank[i] : -1;
     c.h_suppress.assign((size_t)s.V, 0);
     for (int i = 0; i < n_suppress; ++i)
         if (suppress[i] >= 0 && suppress[i] < s.V) c.h_suppress[suppress[i]] = 1;
-    if (!dev_alloc(&c.d_suppress, (size_t)s.V)) return;
+    // the flag buffer is kept and overwritten in place (captured graphs hold its address); it only moves when the vocabulary grows
+    if ((!c.d_suppress || c.suppress_cap < (size_t)s.V) && !dev_alloc(&c.d_suppress, (size_t)s.V)) return;
+    c.suppress_cap = std::max(c.suppress_cap, (size_t)s.V);
     B200_CHECK(cudaMemcpy(c.d_suppress, c.h_suppress.data(), (size_t)s.V, cudaMemcpyHostToDevice));
     c.spec.d_suppress = c.d_suppress;
 }

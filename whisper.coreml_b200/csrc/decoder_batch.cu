@@ -90,6 +90,16 @@ __device__ __forceinline__ void db_wait(uint64_t* bar, uint32_t parity) {       
     while (!mbar_try_wait(bar, parity)) if (++spins > (1u << 24)) db_timeout(0);
 }
 
+__device__ __forceinline__ unsigned long long db_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+struct DbDbg {
+    unsigned long long* buf; bool on;
+    __device__ __forceinline__ void mark(int idx) { if (on && idx < DB_DBG_LD) buf[idx] = db_gtimer(); }
+    // sub-marks of ONE probed stage (sub >= 0): indices 600 .. 639
+    int sub;
+    // (clock64: a %globaltimer read costs ~0.3 us, far too much for marks a few hundred cycles apart)
+    __device__ __forceinline__ void smark(int k) { if (on && sub >= 0 && k < 40) buf[600 + k] = (unsigned long long)clock64(); }
+};
+
 // ---- LL words -----------------------------------------------------------------------------------------------------
 typedef unsigned long long u64;
 __device__ __forceinline__ void ll_st(uint2* p, uint32_t payload, uint32_t epoch) {
@@ -131,35 +141,40 @@ __device__ __forceinline__ void ll_wait_sentinels(const uint2* buf, uint32_t epo
 // U items (2 words each) in flight and stores nothing before the batch has fully arrived.
 template <int CONS, int U>
 __device__ __forceinline__ void ll_copy_region(const uint2* __restrict__ src, uint32_t epoch, int n_rows, long row_words, int word0, int items,
-                                               bf16* xs, int ldx, int tid, int where) {
+                                               bf16* xs, int ldx, int tid, int where, DbDbg* dbg = nullptr) {
     int c = tid, r = 0;
     while (c >= items) { c -= items; ++r; }
+    int round = 0;
     while (r < n_rows) {
-        const uint2* p[U];
-        uint2* dst[U];
-        bool v[U];
+        int rc[U];                                     // (row << 16) | item of every load of the batch, -1 = past the end
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            v[u] = r < n_rows;
-            const int rr = v[u] ? r : 0, cc = v[u] ? c : 0;
-            p[u] = src + (long)rr * row_words + word0 + 2 * cc;
-            dst[u] = reinterpret_cast<uint2*>(xs + (long)rr * ldx) + cc;
+            rc[u] = r < n_rows ? (r << 16) | c : -1;
             c += CONS;
             while (c >= items) { c -= items; ++r; }
         }
         u64 w[U][2];
         unsigned spins = 0;
         bool ok;
+        if (dbg) dbg->smark(5 + 4 * round);
         do {
 #pragma unroll
-            for (int u = 0; u < U; ++u) ll_ld2(p[u], w[u][0], w[u][1]);
+            for (int u = 0; u < U; ++u) {
+                const int rr = rc[u] < 0 ? 0 : rc[u] >> 16, cc = rc[u] < 0 ? 0 : rc[u] & 0xffff;
+                ll_ld2(src + (long)rr * row_words + word0 + 2 * cc, w[u][0], w[u][1]);
+            }
+            if (dbg) dbg->smark(6 + 4 * round);
             ok = true;
 #pragma unroll
             for (int u = 0; u < U; ++u) ok = ok & ll_good(w[u][0], epoch) & ll_good(w[u][1], epoch);
             if (!ok) ll_pause(spins, where);
         } while (!ok);
+        if (dbg) { dbg->smark(7 + 4 * round); if (dbg->on && dbg->sub >= 0) dbg->buf[639] = spins; }
 #pragma unroll
-        for (int u = 0; u < U; ++u) if (v[u]) *dst[u] = make_uint2((uint32_t)w[u][0], (uint32_t)w[u][1]);
+        for (int u = 0; u < U; ++u)
+            if (rc[u] >= 0) reinterpret_cast<uint2*>(xs + (long)(rc[u] >> 16) * ldx)[rc[u] & 0xffff] = make_uint2((uint32_t)w[u][0], (uint32_t)w[u][1]);
+        if (dbg) dbg->smark(8 + 4 * round);
+        ++round;
     }
 }
 
@@ -185,12 +200,6 @@ struct DbSmem {
     uint64_t* full; uint64_t* empty;
     int ldx;
 };
-__device__ __forceinline__ unsigned long long db_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-struct DbDbg {
-    unsigned long long* buf; bool on;
-    __device__ __forceinline__ void mark(int idx) { if (on && idx < DB_DBG_LD) buf[idx] = db_gtimer(); }
-};
-
 // row r of the step -> index of its token history / slot-table row / physical KV slot
 __device__ __forceinline__ int db_trow(const DbArgs& a, int r) { const int w = r / a.nbw; return w * a.slot_stride + (r - w * a.nbw); }
 
@@ -200,24 +209,38 @@ __device__ __forceinline__ int db_trow(const DbArgs& a, int r) { const int w = r
 // residual) is fetched BEFORE the MMA loop so that its latency hides behind the weight stream.
 enum { DB_EPI_LL_F32 = 0, DB_EPI_LL_GELU_BF16 = 1, DB_EPI_LOGITS = 2 };
 enum { DB_RES_NONE = 0, DB_RES_LL = 1, DB_RES_EMBED = 2, DB_RES_XIN = 3 };
+enum { DBS_QKV = 0, DBS_SA, DBS_OUT, DBS_CQ, DBS_CA, DBS_CO, DBS_M1, DBS_M2, DBS_VOCAB };
+// The stage descriptor is three registers (stage, layer, epoch); everything else - bias, residual source, output buffers - is
+// looked up in constant memory (the model descriptor, the kernel arguments) at the point of use, so that nothing but the
+// accumulators is live across the MMA loop (the kernel has 224 registers per consumer thread to work with).
 struct DbGemv {
+    int st, l;
     int n_tiles, n_kc, vcta;
-    int epi;
-    const float* bias;          // [N] or nullptr
-    int res_mode; const uint2* res_ll; uint32_t res_epoch;      // residual: LL fp32 [R][ld_out]
-    uint2* out_ll; float* out_f32; long ld_out;
-    uint2* out_llb;             // DB_EPI_LL_F32: the same outputs again as bf16x2 LL words (LayerNorm input of the next stage) or nullptr
-    int n_valid;                // outputs >= n_valid are not stored
-    uint32_t epoch;
-    // K chunks: the activation columns [c * chunk_kc * 32, ...) are copied from chunk_src (bf16x2 LL rows of chunk_row_words words)
-    // right before the chunk's first slot (MLP2: the hidden row does not fit shared memory for many rows); nullptr = the
-    // prologue has staged all K columns
-    const uint2* chunk_src; long chunk_row_words; int chunk_kc; uint32_t chunk_epoch;
+    uint32_t ep;                 // this layer's epoch; the layer below wrote ep - 1
+    int chunk_kc;                // K blocks of the activations staged at a time (MLP2), else n_kc
+    __device__ __forceinline__ int epi() const { return st == DBS_M1 ? DB_EPI_LL_GELU_BF16 : st == DBS_VOCAB ? DB_EPI_LOGITS : DB_EPI_LL_F32; }
+    __device__ __forceinline__ const float* bias() const {
+        const DbLayer& L = c_db.layers[l];
+        return st == DBS_QKV ? L.qkv_b : st == DBS_OUT ? L.attn_out_b : st == DBS_CQ ? L.cross_q_b : st == DBS_CO ? L.cross_out_b
+             : st == DBS_M1 ? L.mlp1_b : st == DBS_M2 ? L.mlp2_b : nullptr;
+    }
+    __device__ __forceinline__ int res_mode(const DbArgs& a) const {
+        return st == DBS_OUT ? (l == 0 ? (a.x_in ? DB_RES_XIN : DB_RES_EMBED) : DB_RES_LL) : (st == DBS_CO || st == DBS_M2) ? DB_RES_LL : DB_RES_NONE;
+    }
+    __device__ __forceinline__ const uint2* res_ll(const DbArgs& a) const { return st == DBS_OUT ? a.ll_x3 : st == DBS_CO ? a.ll_x1 : a.ll_x2; }
+    __device__ __forceinline__ uint32_t res_epoch() const { return st == DBS_OUT ? ep - 1u : ep; }
+    __device__ __forceinline__ uint2* out_ll(const DbArgs& a) const {
+        return st == DBS_QKV ? a.ll_qkv : st == DBS_OUT ? a.ll_x1 : st == DBS_CQ ? a.ll_q : st == DBS_CO ? a.ll_x2 : st == DBS_M1 ? a.ll_hid : a.ll_x3;
+    }
+    // DB_EPI_LL_F32 stages whose outputs feed a LayerNorm publish them again as bf16x2 LL words
+    __device__ __forceinline__ uint2* out_llb(const DbArgs& a) const { return st == DBS_OUT ? a.ll_x1b : st == DBS_CO ? a.ll_x2b : st == DBS_M2 ? a.ll_x3b : nullptr; }
+    __device__ __forceinline__ long ld_out(const DbArgs& a) const { return st == DBS_QKV ? 3L * c_db.d : st == DBS_M1 ? 4L * c_db.d : st == DBS_VOCAB ? a.ld_logits : (long)c_db.d; }
+    __device__ __forceinline__ int n_valid() const { return st == DBS_QKV ? 3 * c_db.d : st == DBS_M1 ? 4 * c_db.d : st == DBS_VOCAB ? c_db.V : c_db.d; }
 };
 
 template <int NT, int CW>
 __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, int& red_buf, const DbGemv& g, const DbArgs& a, int R,
-                                              int nctas, int warp, int lane) {
+                                              int nctas, int warp, int lane, DbDbg& dbg) {
     using C = DbCfg<NT, CW>;
     const DbModel& M = c_db;
     const int gq = lane >> 2, tq = lane & 3, tid = warp * 32 + lane;
@@ -230,15 +253,18 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, in
         for (int p = 0; p < C::PASSES; ++p) {
             const int idx = tid + p * C::CONS, r = idx >> 4, n = t * 16 + (idx & 15);
             add[p] = 0.f;
-            if (r < R && n < g.n_valid) {
-                if (g.bias) add[p] = __ldg(g.bias + n);
-                if (g.res_mode == DB_RES_LL) add[p] += __uint_as_float(ll_wait_word(g.res_ll + (long)r * g.ld_out + n, g.res_epoch, 1));
-                else if (g.res_mode == DB_RES_EMBED) {
+            if (r < R && n < g.n_valid()) {
+                const float* bias = g.bias();
+                const int res_mode = g.res_mode(a);
+                if (bias) add[p] = __ldg(bias + n);
+                if (res_mode == DB_RES_LL) add[p] += __uint_as_float(ll_wait_word(g.res_ll(a) + (long)r * M.d + n, g.res_epoch(), 1));
+                else if (res_mode == DB_RES_EMBED) {
                     const int pos = sm.spos[r / a.nbw];
                     add[p] += __bfloat162float(M.tok_emb[(long)a.tokens[db_trow(a, r) * DEC_TOK_LD + pos] * M.d + n]) + __ldg(M.pos_emb + (long)pos * M.d + n);
-                } else if (g.res_mode == DB_RES_XIN) add[p] += __ldg(a.x_in + (long)r * M.d + n);
+                } else if (res_mode == DB_RES_XIN) add[p] += __ldg(a.x_in + (long)r * M.d + n);
             }
         }
+        dbg.smark(20 + 4 * (t - u0));
         float acc[NT][2][4];
 #pragma unroll
         for (int j = 0; j < NT; ++j)
@@ -247,40 +273,40 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, in
         for (int c0 = 0, nblk = 0; c0 < g.n_kc; c0 += nblk) {
             const int cin = c0 % g.chunk_kc;                            // first block of the slot within the staged columns
             nblk = db_slot_blocks(c0, g.n_kc, g.chunk_kc);
-            if (g.chunk_src && cin == 0 && !(g.chunk_kc >= g.n_kc && t > u0)) {   // a new K chunk of the activations (one chunk: staged once)
+            if (g.st == DBS_M2 && cin == 0 && !(g.chunk_kc >= g.n_kc && t > u0)) {   // a new K chunk of the MLP hidden row (one chunk: staged once)
                 csync<C::CONS>();                                       // everybody is done with the previous chunk
                 const int word0 = c0 * 16, n_words = min(g.chunk_kc, g.n_kc - c0) * 16;
-                ll_wait_sentinels<C::CONS>(g.chunk_src, g.chunk_epoch, g.chunk_row_words, word0, n_words, 8, R - 1, R, tid, 13);
-                ll_copy_region<C::CONS, 4>(g.chunk_src, g.chunk_epoch, R, g.chunk_row_words, word0, n_words / 2, sm.xs, sm.ldx, tid, 3);
+                ll_wait_sentinels<C::CONS>(a.ll_hid, g.ep, 2L * M.d, word0, n_words, 8, R - 1, R, tid, 13);
+                ll_copy_region<C::CONS, 9>(a.ll_hid, g.ep, R, 2L * M.d, word0, n_words / 2, sm.xs, sm.ldx, tid, 3);
                 csync<C::CONS>();
             }
             const uint4* sl = reinterpret_cast<const uint4*>(sm.ring + (size_t)ring.slot * DB_SLOT) + lane;
             const bf16* xk = xrow + cin * 32;
             db_wait(&sm.full[ring.slot], ring.phase);
+            constexpr int BPW = (DB_SLOT_BLOCKS + CW - 1) / CW, QB = BPW <= 6 ? BPW : 5;      // blocks per warp and slot; per batch
 #pragma unroll
-            for (int q0 = 0; q0 < DB_SLOT_BLOCKS / CW; q0 += 5) {          // batches of five blocks per warp
-                uint4 lo[5], hi[5];
+            for (int q0 = 0; q0 < BPW; q0 += QB) {
+                uint4 lo[QB], hi[QB];
 #pragma unroll
-                for (int q = 0; q < 5; ++q) {
+                for (int q = 0; q < QB; ++q) {
                     const int blk = warp + CW * (q0 + q);
                     if (blk < nblk) { lo[q] = sl[blk * 64]; hi[q] = sl[blk * 64 + 32]; }
                 }
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
-                    constexpr int XB = NT <= 2 ? 5 : 1;                 // activation fragments fetched ahead of their MMAs (register budget)
-                    if (XB == 5) {
-                        uint4 xb[5];
+                    if (NT <= 2) {                                      // activation fragments fetched ahead of their MMAs (register budget)
+                        uint4 xb[QB];
 #pragma unroll
-                        for (int q = 0; q < 5; ++q) {
+                        for (int q = 0; q < QB; ++q) {
                             const int blk = warp + CW * (q0 + q);
                             if (blk < nblk) xb[q] = *reinterpret_cast<const uint4*>(xk + (long)j * 8 * sm.ldx + blk * 32);
                         }
 #pragma unroll
-                        for (int q = 0; q < 5; ++q)
+                        for (int q = 0; q < QB; ++q)
                             if (warp + CW * (q0 + q) < nblk) db_mma(acc[j][q & 1], lo[q], hi[q], xb[q]);
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 5; ++q) {
+                        for (int q = 0; q < QB; ++q) {
                             const int blk = warp + CW * (q0 + q);
                             if (blk < nblk) db_mma(acc[j][q & 1], lo[q], hi[q], *reinterpret_cast<const uint4*>(xk + (long)j * 8 * sm.ldx + blk * 32));
                         }
@@ -291,6 +317,7 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, in
             if (lane == 0) mbar_arrive(&sm.empty[ring.slot]);
             ring.advance();
         }
+        dbg.smark(21 + 4 * (t - u0));
         float* rw = sm.red + red_buf * (CW * NT * 128) + warp * (NT * 128);
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
@@ -299,10 +326,13 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, in
             r[(gq + 8) * 8 + tq * 2] = acc[j][0][2] + acc[j][1][2]; r[(gq + 8) * 8 + tq * 2 + 1] = acc[j][0][3] + acc[j][1][3];
         }
         csync<C::CONS>();
+        dbg.smark(22 + 4 * (t - u0));
 #pragma unroll
         for (int p = 0; p < C::PASSES; ++p) {
             const int idx = tid + p * C::CONS, r = idx >> 4, o = idx & 15, n = t * 16 + o;
-            const bool owner = r < R && n < g.n_valid;
+            const bool owner = r < R && n < g.n_valid();
+            const long ld_out = g.ld_out(a);
+            const int epi = g.epi();
             const float* rr = sm.red + red_buf * (CW * NT * 128) + (r >> 3) * 128 + o * 8 + (r & 7);
             float v = add[p];
             if (idx < C::ROWS * 16) {
@@ -311,195 +341,170 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, in
                 for (int w = 0; w < CW; ++w) s += rr[w * (NT * 128)];
                 v += s;
             }
-            if (g.epi == DB_EPI_LL_GELU_BF16) {
+            if (epi == DB_EPI_LL_GELU_BF16) {
                 v = gelu_erf(v);
                 const float nxt = __shfl_down_sync(0xffffffffu, v, 1);          // lanes are (row, o): o + 1 is the next lane
-                if (owner && !(o & 1)) ll_st(g.out_ll + ((long)r * g.ld_out + n) / 2, pack_bf16(v, nxt), g.epoch);
-            } else if (g.epi == DB_EPI_LL_F32) {
-                if (owner) ll_st(g.out_ll + (long)r * g.ld_out + n, __float_as_uint(v), g.epoch);
-                if (g.out_llb) {                                      // (stage uniform)
+                if (owner && !(o & 1)) ll_st(g.out_ll(a) + ((long)r * ld_out + n) / 2, pack_bf16(v, nxt), g.ep);
+            } else if (epi == DB_EPI_LL_F32) {
+                if (owner) ll_st(g.out_ll(a) + (long)r * ld_out + n, __float_as_uint(v), g.ep);
+                uint2* out_llb = g.out_llb(a);
+                if (out_llb) {                                        // (stage uniform)
                     const float nxt = __shfl_down_sync(0xffffffffu, v, 1);
-                    if (owner && !(o & 1)) ll_st(g.out_llb + ((long)r * g.ld_out + n) / 2, pack_bf16(v, nxt), g.epoch);
+                    if (owner && !(o & 1)) ll_st(out_llb + ((long)r * ld_out + n) / 2, pack_bf16(v, nxt), g.ep);
                 }
             } else if (owner) {
-                __stcg(g.out_f32 + (long)r * g.ld_out + n, v);
+                __stcg(a.logits + (long)r * ld_out + n, v);
             }
         }
+        dbg.smark(23 + 4 * (t - u0));
         if (C::RED_BUFS == 2) red_buf ^= 1;           // the next unit reduces through the other buffer: one barrier per unit
         else csync<C::CONS>();
     }
 }
 
 // ---- prologue: LayerNorm of the residual stream into the bf16 activation rows -------------------------------------------
-// Every thread owns 16-byte items (4 columns) c = tid + CONS * i of every row.  Pass 1 fetches them - token + position
-// embeddings (or x_in), or bf16x2 LL words, DB_G rows in flight - adds them into the row's sum and sum of squares in fp32
-// and parks them in the row as the bf16 pairs they are (the embedding sums are rounded to bf16 here; every later LayerNorm
-// input arrives rounded the same way).  Row statistics are combined across warps through shared memory; pass 2 normalises
-// the thread's own items in place.  gamma | beta arrive through the ring.
+// A warp owns whole rows (rows warp, warp + CW, ...), two per round: every lane fetches its 16-byte items (4 columns) of
+// both rows - token + position embeddings (or x_in), or bf16x2 LL words, up to 20 loads in flight - the row statistics
+// are two butterfly sums inside the warp, and the lane normalises its own items straight from registers into the bf16
+// row.  No staging pass, no cross-warp reduction; gamma | beta arrive through the ring and are read per item.
 enum { DB_PRO_EMBED = 0, DB_PRO_LL = 1 };
+constexpr int DB_LPR = 10;                            // 16-byte items per lane and row (d <= 1280)
 template <int NT, int CW>
 __device__ __forceinline__ void db_prologue_ln(const DbSmem& sm, DbRing& ring, const DbArgs& a, int R, int mode, const uint2* __restrict__ x_ll,
-                                               uint32_t epoch, int warp, int lane) {
+                                               uint32_t epoch, int warp, int lane, DbDbg& dbg) {
     using C = DbCfg<NT, CW>;
     const DbModel& M = c_db;
     const int d = M.d, tid = warp * 32 + lane, items = d >> 2, row_words = d >> 1;
-    float* part = sm.red;                                                  // [CW][ROWS][sum, sum of squares]
+    dbg.smark(0);
     csync<C::CONS>();                                                      // the previous stage is done with xs / red
-    bool v[C::IPR];
-    int cc[C::IPR];
-#pragma unroll
-    for (int i = 0; i < C::IPR; ++i) { v[i] = tid + i * C::CONS < items; cc[i] = v[i] ? tid + i * C::CONS : 0; }   // out of range: re-read item 0
+    dbg.smark(1);
     if (mode == DB_PRO_EMBED) {
         if (!a.x_in) {
             if (tid < R) sm.stok[tid] = a.tokens[db_trow(a, tid) * DEC_TOK_LD + sm.spos[tid / a.nbw]];
             csync<C::CONS>();
         }
+    } else {
+        ll_wait_sentinels<C::CONS>(x_ll, epoch, row_words, 0, row_words, 8, R - 1, R, tid, 12);   // written by 16-column GEMV tiles (8 words)
+    }
+    dbg.smark(2);
+    db_wait(&sm.full[ring.slot], ring.phase);                              // gamma | beta: one slot ahead of the stage's tiles
+    dbg.smark(3);
+    const float4* gsl = reinterpret_cast<const float4*>(sm.ring + (size_t)ring.slot * DB_SLOT);
+    const float inv_d = __fdividef(1.f, (float)d);       // (an IEEE division would bring a slow-path subroutine: see db_timeout)
+    if (mode == DB_PRO_EMBED) {
+        // opens every step (nothing hides it): one row per round, the row's fp32 sums stay in registers
 #pragma unroll 1
-        for (int r0 = 0; r0 < R; r0 += DB_G) {
-            float4 xv[DB_G][C::IPR];
+        for (int r = warp; r < R; r += CW) {
+            float x[DB_LPR][4];
             if (a.x_in) {
+                const float4* xp = reinterpret_cast<const float4*>(a.x_in + (long)r * d);
 #pragma unroll
-                for (int q = 0; q < DB_G; ++q) {
-                    const float4* xp = reinterpret_cast<const float4*>(a.x_in + (long)min(r0 + q, R - 1) * d);
-#pragma unroll
-                    for (int i = 0; i < C::IPR; ++i) xv[q][i] = __ldg(xp + cc[i]);
+                for (int i = 0; i < DB_LPR; ++i) {
+                    const int c = lane + 32 * i;
+                    const float4 v = c < items ? __ldg(xp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    x[i][0] = v.x; x[i][1] = v.y; x[i][2] = v.z; x[i][3] = v.w;
                 }
             } else {
-                uint2 tv[DB_G][C::IPR];
+                uint2 tv[DB_LPR];
+                const uint2* tp = reinterpret_cast<const uint2*>(M.tok_emb + (long)sm.stok[r] * d);
+                const float4* pp = reinterpret_cast<const float4*>(M.pos_emb + (long)sm.spos[r / a.nbw] * d);
 #pragma unroll
-                for (int q = 0; q < DB_G; ++q) {
-                    const int r = min(r0 + q, R - 1);
-                    const uint2* tp = reinterpret_cast<const uint2*>(M.tok_emb + (long)sm.stok[r] * d);
-                    const float4* pp = reinterpret_cast<const float4*>(M.pos_emb + (long)sm.spos[r / a.nbw] * d);
-#pragma unroll
-                    for (int i = 0; i < C::IPR; ++i) { tv[q][i] = __ldg(tp + cc[i]); xv[q][i] = __ldg(pp + cc[i]); }
+                for (int i = 0; i < DB_LPR; ++i) {
+                    const int c = lane + 32 * i;
+                    const bool v = c < items;
+                    tv[i] = v ? __ldg(tp + c) : make_uint2(0u, 0u);
+                    const float4 pv = v ? __ldg(pp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    x[i][0] = pv.x; x[i][1] = pv.y; x[i][2] = pv.z; x[i][3] = pv.w;
                 }
 #pragma unroll
-                for (int q = 0; q < DB_G; ++q)
-#pragma unroll
-                    for (int i = 0; i < C::IPR; ++i) {
-                        xv[q][i].x += bf16lo(tv[q][i].x); xv[q][i].y += bf16hi(tv[q][i].x);
-                        xv[q][i].z += bf16lo(tv[q][i].y); xv[q][i].w += bf16hi(tv[q][i].y);
-                    }
+                for (int i = 0; i < DB_LPR; ++i) { x[i][0] += bf16lo(tv[i].x); x[i][1] += bf16hi(tv[i].x); x[i][2] += bf16lo(tv[i].y); x[i][3] += bf16hi(tv[i].y); }
             }
-            float s1[DB_G], s2[DB_G];
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-            for (int q = 0; q < DB_G; ++q) {
-                uint2* dst = reinterpret_cast<uint2*>(sm.xs + (long)min(r0 + q, R - 1) * sm.ldx);
-                s1[q] = 0.f; s2[q] = 0.f;
-#pragma unroll
-                for (int i = 0; i < C::IPR; ++i)
-                    if (v[i]) {
-                        const float4 x = xv[q][i];
-                        dst[cc[i]] = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
-                        s1[q] += (x.x + x.y) + (x.z + x.w);
-                        s2[q] = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, s2[q]))));
-                    }
+            for (int i = 0; i < DB_LPR; ++i) {                             // items past the row are zeros: they add nothing
+                s1 += (x[i][0] + x[i][1]) + (x[i][2] + x[i][3]);
+                s2 = fmaf(x[i][0], x[i][0], fmaf(x[i][1], x[i][1], fmaf(x[i][2], x[i][2], fmaf(x[i][3], x[i][3], s2))));
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
+            for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+            const float mean = s1 * inv_d, rstd = rsqrtf(fmaxf(s2 * inv_d - mean * mean, 0.f) + 1e-5f);
+            uint2* row = reinterpret_cast<uint2*>(sm.xs + (long)r * sm.ldx);
 #pragma unroll
-                for (int q = 0; q < DB_G; ++q) { s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o); s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], o); }
-            if (lane == 0) {
-#pragma unroll
-                for (int q = 0; q < DB_G; ++q)
-                    if (r0 + q < R) *reinterpret_cast<float2*>(part + (warp * C::ROWS + r0 + q) * 2) = make_float2(s1[q], s2[q]);
+            for (int i = 0; i < DB_LPR; ++i) {
+                const int c = lane + 32 * i;
+                if (c < items) {
+                    const float4 ga = gsl[c], be = gsl[items + c];
+                    row[c] = make_uint2(pack_bf16((x[i][0] - mean) * rstd * ga.x + be.x, (x[i][1] - mean) * rstd * ga.y + be.y),
+                                        pack_bf16((x[i][2] - mean) * rstd * ga.z + be.z, (x[i][3] - mean) * rstd * ga.w + be.w));
+                }
             }
         }
     } else {
-        ll_wait_sentinels<C::CONS>(x_ll, epoch, row_words, 0, row_words, 8, R - 1, R, tid, 12);   // written by 16-column GEMV tiles (8 words)
 #pragma unroll 1
-        for (int r0 = 0; r0 < R; r0 += DB_G) {
-            u64 w[DB_G][C::IPR][2];
-            const uint2* pr[DB_G];
+        for (int r0 = warp; r0 < R; r0 += 2 * CW) {
+            const int r1 = r0 + CW < R ? r0 + CW : r0;                     // a warp without a second row repeats its first
+            uint32_t px[2][DB_LPR][2];                                     // the bf16x2 payloads of the two rows
+            {
+                const uint2* p0 = x_ll + (long)r0 * row_words;
+                const uint2* p1 = x_ll + (long)r1 * row_words;
+                u64 w[2][DB_LPR][2];                                       // all 20 loads are issued before the first epoch is looked at
+                unsigned spins = 0;
+                bool ok;
+                do {
 #pragma unroll
-            for (int q = 0; q < DB_G; ++q) pr[q] = x_ll + (long)min(r0 + q, R - 1) * row_words;      // rows past R re-read the last row
-            unsigned spins = 0;
-            bool ok;
-            do {
+                    for (int i = 0; i < DB_LPR; ++i) {
+                        const int c = lane + 32 * i < items ? lane + 32 * i : 0;    // past the row: re-read item 0
+                        ll_ld2(p0 + 2 * c, w[0][i][0], w[0][i][1]); ll_ld2(p1 + 2 * c, w[1][i][0], w[1][i][1]);
+                    }
+                    ok = true;
 #pragma unroll
-                for (int q = 0; q < DB_G; ++q)
+                    for (int i = 0; i < DB_LPR; ++i) ok = ok & ll_good(w[0][i][0], epoch) & ll_good(w[0][i][1], epoch) & ll_good(w[1][i][0], epoch) & ll_good(w[1][i][1], epoch);
+                    if (!ok) ll_pause(spins, 2);
+                } while (!ok);
+                dbg.smark(4 + 2 * ((r0 - warp) / (2 * CW)));
 #pragma unroll
-                    for (int i = 0; i < C::IPR; ++i) ll_ld2(pr[q] + 2 * cc[i], w[q][i][0], w[q][i][1]);
-                ok = true;
+                for (int i = 0; i < DB_LPR; ++i) {
+                    px[0][i][0] = (uint32_t)w[0][i][0]; px[0][i][1] = (uint32_t)w[0][i][1]; px[1][i][0] = (uint32_t)w[1][i][0]; px[1][i][1] = (uint32_t)w[1][i][1];
+                }
+            }
+            float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
 #pragma unroll
-                for (int q = 0; q < DB_G; ++q)
+            for (int q = 0; q < 2; ++q)
 #pragma unroll
-                    for (int i = 0; i < C::IPR; ++i) ok = ok & ll_good(w[q][i][0], epoch) & ll_good(w[q][i][1], epoch);
-                if (!ok) ll_pause(spins, 2);
-            } while (!ok);
-            float s1[DB_G], s2[DB_G];
-#pragma unroll
-            for (int q = 0; q < DB_G; ++q) {
-                uint2* dst = reinterpret_cast<uint2*>(sm.xs + (long)min(r0 + q, R - 1) * sm.ldx);
-                s1[q] = 0.f; s2[q] = 0.f;
-#pragma unroll
-                for (int i = 0; i < C::IPR; ++i)
-                    if (v[i]) {
-                        const uint32_t p0 = (uint32_t)w[q][i][0], p1 = (uint32_t)w[q][i][1];
-                        dst[cc[i]] = make_uint2(p0, p1);
-                        const float x0 = bf16lo(p0), x1 = bf16hi(p0), x2 = bf16lo(p1), x3 = bf16hi(p1);
+                for (int i = 0; i < DB_LPR; ++i)
+                    if (lane + 32 * i < items) {
+                        const float x0 = bf16lo(px[q][i][0]), x1 = bf16hi(px[q][i][0]), x2 = bf16lo(px[q][i][1]), x3 = bf16hi(px[q][i][1]);
                         s1[q] += (x0 + x1) + (x2 + x3);
                         s2[q] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, s2[q]))));
                     }
-            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                for (int q = 0; q < DB_G; ++q) { s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o); s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], o); }
-            if (lane == 0) {
+                for (int q = 0; q < 2; ++q) { s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o); s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], o); }
 #pragma unroll
-                for (int q = 0; q < DB_G; ++q)
-                    if (r0 + q < R) *reinterpret_cast<float2*>(part + (warp * C::ROWS + r0 + q) * 2) = make_float2(s1[q], s2[q]);
-            }
-        }
-    }
-    csync<C::CONS>();
-    if (tid < R) {                                                         // one thread per row: (mean, rstd)
-        float s1 = 0.f, s2 = 0.f;
+            for (int q = 0; q < 2; ++q) {
+                if (q == 1 && r1 == r0) break;                             // (warp uniform)
+                const float mean = s1[q] * inv_d, rstd = rsqrtf(fmaxf(s2[q] * inv_d - mean * mean, 0.f) + 1e-5f);
+                uint2* row = reinterpret_cast<uint2*>(sm.xs + (long)(q ? r1 : r0) * sm.ldx);
 #pragma unroll
-        for (int w = 0; w < CW; ++w) { const float2 p = *reinterpret_cast<const float2*>(part + (w * C::ROWS + tid) * 2); s1 += p.x; s2 += p.y; }
-        const float mean = s1 / d;
-        *reinterpret_cast<float2*>(sm.rowstat + 2 * tid) = make_float2(mean, rsqrtf(fmaxf(s2 / d - mean * mean, 0.f) + 1e-5f));
-    }
-    db_wait(&sm.full[ring.slot], ring.phase);                              // gamma | beta: one slot ahead of the stage's tiles
-    csync<C::CONS>();
-    {
-        float4 ga[C::IPR], be[C::IPR];
-        const float4* gsl = reinterpret_cast<const float4*>(sm.ring + (size_t)ring.slot * DB_SLOT);
-#pragma unroll
-        for (int i = 0; i < C::IPR; ++i) { ga[i] = gsl[cc[i]]; be[i] = gsl[items + cc[i]]; }
-#pragma unroll 1
-        for (int r0 = 0; r0 < R; r0 += DB_G) {
-            uint2 xv[DB_G][C::IPR];
-            float2 ms[DB_G];
-#pragma unroll
-            for (int q = 0; q < DB_G; ++q) {
-                const int r = min(r0 + q, R - 1);
-                const uint2* row = reinterpret_cast<const uint2*>(sm.xs + (long)r * sm.ldx);
-#pragma unroll
-                for (int i = 0; i < C::IPR; ++i) xv[q][i] = row[cc[i]];
-                ms[q] = *reinterpret_cast<const float2*>(sm.rowstat + 2 * r);
-            }
-#pragma unroll
-            for (int q = 0; q < DB_G; ++q) {
-                if (r0 + q < R) {
-                    uint2* row = reinterpret_cast<uint2*>(sm.xs + (long)(r0 + q) * sm.ldx);
-#pragma unroll
-                    for (int i = 0; i < C::IPR; ++i)
-                        if (v[i]) {
-                            const float mean = ms[q].x, rstd = ms[q].y;
-                            row[cc[i]] = make_uint2(pack_bf16((bf16lo(xv[q][i].x) - mean) * rstd * ga[i].x + be[i].x, (bf16hi(xv[q][i].x) - mean) * rstd * ga[i].y + be[i].y),
-                                                    pack_bf16((bf16lo(xv[q][i].y) - mean) * rstd * ga[i].z + be[i].z, (bf16hi(xv[q][i].y) - mean) * rstd * ga[i].w + be[i].w));
-                        }
+                for (int i = 0; i < DB_LPR; ++i) {
+                    const int c = lane + 32 * i;
+                    if (c < items) {
+                        const float4 ga = gsl[c], be = gsl[items + c];
+                        row[c] = make_uint2(pack_bf16((bf16lo(px[q][i][0]) - mean) * rstd * ga.x + be.x, (bf16hi(px[q][i][0]) - mean) * rstd * ga.y + be.y),
+                                            pack_bf16((bf16lo(px[q][i][1]) - mean) * rstd * ga.z + be.z, (bf16hi(px[q][i][1]) - mean) * rstd * ga.w + be.w));
+                    }
                 }
             }
+            dbg.smark(5 + 2 * ((r0 - warp) / (2 * CW)));
         }
     }
+    dbg.smark(18);
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[ring.slot]);
     ring.advance();
     csync<C::CONS>();
+    dbg.smark(19);
 }
 
 // ---- self-attention of the new token, unit = (row, head) ------------------------------------------------------------------
@@ -593,7 +598,7 @@ __device__ __forceinline__ void db_stage_self_attn(const DbSmem& sm, const DbArg
             float e0 = 0.f, e1 = 0.f;
 #pragma unroll
             for (int w = 0; w < CW; ++w) { const float2 p = *reinterpret_cast<const float2*>(sred + w * 64 + 2 * tid); e0 += p.x; e1 += p.y; }
-            ll_st(a.ll_att + ((long)r * d + h * 64) / 2 + tid, pack_bf16(e0 / lsum, e1 / lsum), ep);
+            ll_st(a.ll_att + ((long)r * d + h * 64) / 2 + tid, pack_bf16(__fdividef(e0, lsum), __fdividef(e1, lsum)), ep);
         }
     }
 }
@@ -716,7 +721,7 @@ __device__ __forceinline__ void db_stage_cross_attn(const DbSmem& sm, DbRing& ri
                     const float wq = __expf(__uint_as_float((uint32_t)rm[q]) - mm);
                     ll = fmaf(__uint_as_float((uint32_t)rl[q]), wq, ll); oo = fmaf(__uint_as_float((uint32_t)ro[q]), wq, oo);
                 }
-                const float o = oo / ll;
+                const float o = __fdividef(oo, ll);
                 const float nxt = __shfl_down_sync(0xffffffffu, o, 1);
                 if (!(c & 1)) ll_st(a.ll_catt + ((long)(w * nbw + b) * d + h * 64 + c) / 2, pack_bf16(o, nxt), ep);
             }
@@ -725,7 +730,6 @@ __device__ __forceinline__ void db_stage_cross_attn(const DbSmem& sm, DbRing& ri
 }
 
 // ---- the stage table: stage `it` of the step (8 per layer + the vocabulary projection) ----------------------------------------
-enum { DBS_QKV = 0, DBS_SA, DBS_OUT, DBS_CQ, DBS_CA, DBS_CO, DBS_M1, DBS_M2, DBS_VOCAB };
 struct DbStageDesc {                   // what the producer needs: the weight matrix of a GEMV stage and who owns which tile
     const bf16* w; int n_tiles, n_kc, vcta;
     const float *ln_g, *ln_b;          // LayerNorm in front of the stage (gamma | beta ride in one slot) or nullptr
@@ -846,12 +850,11 @@ __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsig
     const int n_stages = M.Ld * 8 + (a.no_vocab ? 0 : 1);
     DbRing ring{0, 0, a.n_slots};
     int red_buf = 0;
-    DbDbg dbg{a.dbg + (size_t)cta * DB_DBG_LD, a.dbg != nullptr && tid == 0};
+    DbDbg dbg{a.dbg + (size_t)cta * DB_DBG_LD, a.dbg != nullptr && tid == 0, -1};
     dbg.mark(0);
 
     for (int it = 0; it < n_stages; ++it) {
         const int l = it >> 3, st = it == M.Ld * 8 ? DBS_VOCAB : (it & 7);
-        const DbLayer& L = M.layers[l < M.Ld ? l : 0];
         const uint32_t ep = seq * 64u + (uint32_t)l + 1u, ep_prev = ep - 1u;      // ep_prev: x3 of the layer below
         if (st == DBS_SA) {
             dbg.mark(2 * it + 1);
@@ -866,38 +869,35 @@ __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsig
             dbg.mark(2 * it + 2);
             continue;
         }
-        const DbStageDesc sd = db_stage_desc(st, l < M.Ld ? l : 0, cta, nctas);
-        DbGemv g{sd.n_tiles, sd.n_kc, sd.vcta, DB_EPI_LL_F32, nullptr, DB_RES_NONE, nullptr, ep, nullptr, nullptr, (long)d, nullptr, d, ep,
-                 nullptr, 0, sd.n_kc, ep};
-        const uint2* pro_src = nullptr; uint32_t pro_ep = ep;
-        switch (st) {
-        case DBS_QKV: pro_src = a.ll_x3b; pro_ep = ep_prev; g.bias = L.qkv_b; g.out_ll = a.ll_qkv; g.ld_out = 3L * d; g.n_valid = 3 * d; break;
-        case DBS_OUT:
-            pro_src = a.ll_att; g.bias = L.attn_out_b; g.out_ll = a.ll_x1; g.out_llb = a.ll_x1b;
-            g.res_mode = l == 0 ? (a.x_in ? DB_RES_XIN : DB_RES_EMBED) : DB_RES_LL; g.res_ll = a.ll_x3; g.res_epoch = ep_prev;
-            break;
-        case DBS_CQ: pro_src = a.ll_x1b; g.bias = L.cross_q_b; g.out_ll = a.ll_q; break;
-        case DBS_CO: pro_src = a.ll_catt; g.bias = L.cross_out_b; g.out_ll = a.ll_x2; g.out_llb = a.ll_x2b; g.res_mode = DB_RES_LL; g.res_ll = a.ll_x1; break;
-        case DBS_M1: pro_src = a.ll_x2b; g.epi = DB_EPI_LL_GELU_BF16; g.bias = L.mlp1_b; g.out_ll = a.ll_hid; g.ld_out = 4L * d; g.n_valid = 4 * d; break;
-        case DBS_M2:
-            g.bias = L.mlp2_b; g.out_ll = a.ll_x3; g.out_llb = a.ll_x3b; g.res_mode = DB_RES_LL; g.res_ll = a.ll_x2;
-            g.chunk_src = a.ll_hid; g.chunk_row_words = 2L * d; g.chunk_kc = min(a.xs_cols >> 5, sd.n_kc);
-            break;
-        default:    pro_src = a.ll_x3b; pro_ep = seq * 64u + (uint32_t)M.Ld; g.epi = DB_EPI_LOGITS; g.out_f32 = a.logits; g.ld_out = a.ld_logits; g.n_valid = M.V; break;
-        }
-        int u0, u1;
-        db_range(g.n_tiles, g.vcta, nctas, u0, u1);
-        if (u1 > u0 && st != DBS_M2) {                 // a CTA without a tile in this stage does not read its input at all
-            if (sd.ln_g) db_prologue_ln<NT, CW>(sm, ring, a, R, it == 0 ? DB_PRO_EMBED : DB_PRO_LL, pro_src, pro_ep, warp, lane);
-            else {                                     // attention outputs: 32 words (64 columns) per (row, head)
-                csync<C::CONS>();
-                ll_wait_sentinels<C::CONS>(pro_src, pro_ep, d >> 1, 0, d >> 1, 32, 0, R, tid, 13);
-                ll_copy_region<C::CONS, 4>(pro_src, pro_ep, R, d >> 1, 0, d >> 2, sm.xs, sm.ldx, tid, 3);
-                csync<C::CONS>();
+        dbg.sub = it == a.dbg_stage ? it : -1;
+        {   // prologue first, with as little live state as possible (the stage descriptor is built after it)
+            const DbStageDesc sd = db_stage_desc(st, l < M.Ld ? l : 0, cta, nctas);
+            int u0, u1;
+            db_range(sd.n_tiles, sd.vcta, nctas, u0, u1);
+            if (u1 > u0 && st != DBS_M2) {             // a CTA without a tile in this stage does not read its input at all
+                if (sd.ln_g) {
+                    const uint2* src = st == DBS_CQ ? a.ll_x1b : st == DBS_M1 ? a.ll_x2b : a.ll_x3b;
+                    const uint32_t pep = st == DBS_QKV ? ep_prev : st == DBS_VOCAB ? seq * 64u + (uint32_t)M.Ld : ep;
+                    db_prologue_ln<NT, CW>(sm, ring, a, R, it == 0 ? DB_PRO_EMBED : DB_PRO_LL, src, pep, warp, lane, dbg);
+                } else {                               // attention outputs: 32 words (64 columns) per (row, head)
+                    const uint2* src = st == DBS_OUT ? a.ll_att : a.ll_catt;
+                    dbg.smark(0);
+                    csync<C::CONS>();
+                    dbg.smark(1);
+                    ll_wait_sentinels<C::CONS>(src, ep, d >> 1, 0, d >> 1, 32, 0, R, tid, 13);
+                    dbg.smark(2);
+                    if (a.copy_u == 4) ll_copy_region<C::CONS, 4>(src, ep, R, d >> 1, 0, d >> 2, sm.xs, sm.ldx, tid, 3, &dbg);
+                    else ll_copy_region<C::CONS, 13>(src, ep, R, d >> 1, 0, d >> 2, sm.xs, sm.ldx, tid, 3, &dbg);
+                    dbg.smark(3);
+                    csync<C::CONS>();
+                    dbg.smark(4);
+                }
             }
         }
+        const DbStageDesc sd = db_stage_desc(st, l < M.Ld ? l : 0, cta, nctas);
+        const DbGemv g{st, l < M.Ld ? l : 0, sd.n_tiles, sd.n_kc, sd.vcta, ep, st == DBS_M2 ? min(a.xs_cols >> 5, sd.n_kc) : sd.n_kc};
         dbg.mark(2 * it + 1);
-        db_stage_gemv<NT, CW>(sm, ring, red_buf, g, a, R, nctas, warp, lane);
+        db_stage_gemv<NT, CW>(sm, ring, red_buf, g, a, R, nctas, warp, lane, dbg);
         dbg.mark(2 * it + 2);
     }
     // the last CTA to leave advances the launch sequence number: by then every CTA has read it
@@ -942,7 +942,7 @@ __global__ void __launch_bounds__(DbCfg<NT, CW>::THREADS, 1) decoder_batch_kerne
 void db_set_model(const DbModel& m) { B200_CHECK(cudaMemcpyToSymbol(c_db, &m, sizeof(DbModel))); }
 
 int db_consumer_warps() {
-    static const int cw = [] { const char* e = getenv("B200_STEP_WARPS"); const int v = e ? atoi(e) : 8; return v == 4 ? 4 : 8; }();
+    static const int cw = [] { const char* e = getenv("B200_STEP_WARPS"); const int v = e ? atoi(e) : 7; return v == 4 ? 4 : (v == 8 ? 8 : 7); }();
     return cw;
 }
 
@@ -1009,7 +1009,7 @@ bool db_launch(const DbArgs& a, int n_ctas, cudaStream_t s) {
     const int rows = a.W * a.nbw, nt = (rows + 7) / 8, cw = db_consumer_warps();
     const size_t smem = (size_t)a.ring_offset + (size_t)a.n_slots * DB_SLOT;
 #define DB_CASE(NT_)                                                                                                   \
-    case NT_: return cw == 4 ? db_launch_t<NT_, 4>(a, n_ctas, smem, s) : db_launch_t<NT_, 8>(a, n_ctas, smem, s);
+    case NT_: return cw == 4 ? db_launch_t<NT_, 4>(a, n_ctas, smem, s) : cw == 8 ? db_launch_t<NT_, 8>(a, n_ctas, smem, s) : db_launch_t<NT_, 7>(a, n_ctas, smem, s);
     switch (nt) {
         DB_CASE(1) DB_CASE(2) DB_CASE(3) DB_CASE(4) DB_CASE(5)
     default: record_error("decoder_batch: %d rows", rows); return false;

@@ -50,11 +50,13 @@ struct DbArgs {
     int no_vocab;                        // stop after the last layer (prompt positions whose logits nobody reads)
     unsigned* barrier;                   // [1] CTAs that have left the kernel, [2] launch sequence number
     unsigned long long* dbg;             // optional stage timeline: [n_ctas][DB_DBG_LD] %globaltimer values (0 = not reached)
+    int copy_u;                          // experiment: loads in flight per thread in the activation copies (B200_STEP_COPYU)
+    int dbg_stage;                       // stage index whose inner marks are recorded at 600.. (B200_STEP_PROBE), -1 = none
 };
 
 struct DbGeometry { int nt, xs_cols, xs_rows, ring_offset, n_slots, sa_cap; size_t smem; };
 void db_set_model(const DbModel& m);
-int db_consumer_warps();                               // B200_STEP_WARPS (4 or 8)
+int db_consumer_warps();                               // B200_STEP_WARPS (4, 7 or 8)
 bool db_geometry(int d, int rows, int smem_optin, DbGeometry* g);
 size_t db_ll_words(size_t d, size_t H);
 void db_carve_ll(DbArgs& a, uint2* base, size_t d, size_t H);
