@@ -31,3 +31,12 @@ def exported(name: str, seed: int = 0, logit_scale: float = 1.0):
 def golden(name: str):
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_{name}.npz")
     return np.load(path)
+
+
+def close_library():
+    """The library holds ONE model per process (like the reference's plugin): a test that builds its own model while a
+    module-scoped fixture still has another one loaded would silently run on the fixture's weights (loads are idempotent)."""
+    from whisper_b200 import _lib
+    lib = _lib.load()
+    lib.closeDecoder1(); lib.closeDecoder256(); lib.closeCrossKV(); lib.closeEncoder()
+    _lib.check_errors("close")

@@ -38,7 +38,6 @@ constexpr int DB_SPLIT_TILES = 14;                    // 16-key tiles per cross-
 constexpr int DB_SPLIT_KEYS = DB_SPLIT_TILES * 16;
 static_assert(DB_N_SPLITS == (CROSS_KEYS_PAD / 16 + DB_SPLIT_TILES - 1) / DB_SPLIT_TILES, "key splits");
 constexpr unsigned DB_SPIN_LIMIT = 1u << 22;
-constexpr int DB_G = 5;                               // rows whose loads are in flight together in the LayerNorm prologue
 
 template <int NT, int CW>
 struct DbCfg {
@@ -77,27 +76,23 @@ __device__ __forceinline__ void db_cp_async16(void* smem_dst, const void* gsrc) 
 }
 __device__ __forceinline__ void db_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// A protocol bug traps (-> launch error) instead of hanging the GPU box.  No call and no printf here: a function call
-// reachable from both sides of the setmaxnreg split makes ptxas compile the WHOLE kernel for the smaller register file.
-__device__ unsigned g_db_timeout[4];                  // {where, cta, thread, 1} of the first wait that gave up (b200 reads it after a failed launch)
-__device__ __forceinline__ void db_timeout(int where) {
-    g_db_timeout[0] = (unsigned)where; g_db_timeout[1] = blockIdx.x; g_db_timeout[2] = threadIdx.x; g_db_timeout[3] = 1u;
-    __threadfence_system();
-    asm volatile("trap;");
-}
+// A protocol bug traps (-> launch error) instead of hanging the GPU box.  One instruction: the kernel is instruction-fetch
+// bound (every stage's code runs once per layer from a cold instruction cache), so nothing cold may sit between hot code.
+__device__ __forceinline__ void db_timeout(int) { asm volatile("trap;"); }
 __device__ __forceinline__ void db_wait(uint64_t* bar, uint32_t parity) {         // bounded mbarrier wait
     unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) if (++spins > (1u << 24)) db_timeout(0);
 }
 
 __device__ __forceinline__ unsigned long long db_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-struct DbDbg {
+template <bool ON>
+struct DbDbgT {
     unsigned long long* buf; bool on;
-    __device__ __forceinline__ void mark(int idx) { if (on && idx < DB_DBG_LD) buf[idx] = db_gtimer(); }
-    // sub-marks of ONE probed stage (sub >= 0): indices 600 .. 639
-    int sub;
+    int sub;                                           // sub-marks of ONE probed stage (sub >= 0): indices 600 .. 639
+    __device__ __forceinline__ void mark(int idx) { if (ON && on && idx < DB_DBG_LD) buf[idx] = db_gtimer(); }
     // (clock64: a %globaltimer read costs ~0.3 us, far too much for marks a few hundred cycles apart)
-    __device__ __forceinline__ void smark(int k) { if (on && sub >= 0 && k < 40) buf[600 + k] = (unsigned long long)clock64(); }
+    __device__ __forceinline__ void smark(int k) { if (ON && on && sub >= 0 && k < 40) buf[600 + k] = (unsigned long long)clock64(); }
+    __device__ __forceinline__ void set_sub(int v) { if (ON) sub = v; }
 };
 
 // ---- LL words -----------------------------------------------------------------------------------------------------
@@ -137,44 +132,40 @@ __device__ __forceinline__ void ll_wait_sentinels(const uint2* buf, uint32_t epo
     csync<CONS>();
 }
 // Copies a region of a bf16x2 LL matrix - rows [0, n_rows), words [word0, word0 + 2 * items) of rows `row_words` apart - into
-// the shared-memory activation rows (row r, columns from 0): every thread walks the flattened (row, 16-byte item) space with
-// U items (2 words each) in flight and stores nothing before the batch has fully arrived.
-template <int CONS, int U>
+// the shared-memory activation rows (row r, columns from 0).  A ROLLED loop with four 16-byte items in flight per thread: the
+// kernel is instruction-fetch bound, so the body has to stay a few cache lines long (an unrolled version with 13 loads in
+// flight measured 1.8x slower although it needs a third of the round trips).
+template <int CONS>
 __device__ __forceinline__ void ll_copy_region(const uint2* __restrict__ src, uint32_t epoch, int n_rows, long row_words, int word0, int items,
-                                               bf16* xs, int ldx, int tid, int where, DbDbg* dbg = nullptr) {
+                                               bf16* xs, int ldx, int tid, int where) {
     int c = tid, r = 0;
     while (c >= items) { c -= items; ++r; }
-    int round = 0;
+#pragma unroll 1
     while (r < n_rows) {
-        int rc[U];                                     // (row << 16) | item of every load of the batch, -1 = past the end
+        int rc[4];                                     // (row << 16) | item of every load of the batch, -1 = past the end
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
+        for (int u = 0; u < 4; ++u) {
             rc[u] = r < n_rows ? (r << 16) | c : -1;
             c += CONS;
             while (c >= items) { c -= items; ++r; }
         }
-        u64 w[U][2];
+        u64 w[4][2];
         unsigned spins = 0;
         bool ok;
-        if (dbg) dbg->smark(5 + 4 * round);
         do {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
+            for (int u = 0; u < 4; ++u) {
                 const int rr = rc[u] < 0 ? 0 : rc[u] >> 16, cc = rc[u] < 0 ? 0 : rc[u] & 0xffff;
                 ll_ld2(src + (long)rr * row_words + word0 + 2 * cc, w[u][0], w[u][1]);
             }
-            if (dbg) dbg->smark(6 + 4 * round);
             ok = true;
 #pragma unroll
-            for (int u = 0; u < U; ++u) ok = ok & ll_good(w[u][0], epoch) & ll_good(w[u][1], epoch);
+            for (int u = 0; u < 4; ++u) ok = ok & ll_good(w[u][0], epoch) & ll_good(w[u][1], epoch);
             if (!ok) ll_pause(spins, where);
         } while (!ok);
-        if (dbg) { dbg->smark(7 + 4 * round); if (dbg->on && dbg->sub >= 0) dbg->buf[639] = spins; }
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+        for (int u = 0; u < 4; ++u)
             if (rc[u] >= 0) reinterpret_cast<uint2*>(xs + (long)(rc[u] >> 16) * ldx)[rc[u] & 0xffff] = make_uint2((uint32_t)w[u][0], (uint32_t)w[u][1]);
-        if (dbg) dbg->smark(8 + 4 * round);
-        ++round;
     }
 }
 
@@ -238,9 +229,9 @@ struct DbGemv {
     __device__ __forceinline__ int n_valid() const { return st == DBS_QKV ? 3 * c_db.d : st == DBS_M1 ? 4 * c_db.d : st == DBS_VOCAB ? c_db.V : c_db.d; }
 };
 
-template <int NT, int CW>
+template <int NT, int CW, class Dbg>
 __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, int& red_buf, const DbGemv& g, const DbArgs& a, int R,
-                                              int nctas, int warp, int lane, DbDbg& dbg) {
+                                              int nctas, int warp, int lane, Dbg& dbg) {
     using C = DbCfg<NT, CW>;
     const DbModel& M = c_db;
     const int gq = lane >> 2, tq = lane & 3, tid = warp * 32 + lane;
@@ -277,7 +268,7 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, in
                 csync<C::CONS>();                                       // everybody is done with the previous chunk
                 const int word0 = c0 * 16, n_words = min(g.chunk_kc, g.n_kc - c0) * 16;
                 ll_wait_sentinels<C::CONS>(a.ll_hid, g.ep, 2L * M.d, word0, n_words, 8, R - 1, R, tid, 13);
-                ll_copy_region<C::CONS, 9>(a.ll_hid, g.ep, R, 2L * M.d, word0, n_words / 2, sm.xs, sm.ldx, tid, 3);
+                ll_copy_region<C::CONS>(a.ll_hid, g.ep, R, 2L * M.d, word0, n_words / 2, sm.xs, sm.ldx, tid, 3);
                 csync<C::CONS>();
             }
             const uint4* sl = reinterpret_cast<const uint4*>(sm.ring + (size_t)ring.slot * DB_SLOT) + lane;
@@ -363,36 +354,31 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, in
 }
 
 // ---- prologue: LayerNorm of the residual stream into the bf16 activation rows -------------------------------------------
-// A warp owns whole rows (rows warp, warp + CW, ...), two per round: every lane fetches its 16-byte items (4 columns) of
-// both rows - token + position embeddings (or x_in), or bf16x2 LL words, up to 20 loads in flight - the row statistics
-// are two butterfly sums inside the warp, and the lane normalises its own items straight from registers into the bf16
-// row.  No staging pass, no cross-warp reduction; gamma | beta arrive through the ring and are read per item.
+// LL rows (every LayerNorm but the step's first): every thread owns 16-byte items (4 columns) c = tid + CONS * i of every row.
+// Pass 1 fetches them as bf16x2 LL words, DB_G rows in flight, adds them into the row's sum and sum of squares in fp32 and parks
+// them in the row as the bf16 pairs they are; row statistics are combined across warps through shared memory; pass 2 normalises
+// the thread's own items in place.  The step's first LayerNorm (token + position embeddings, or x_in) is done a row per warp
+// with the fp32 sums in registers: rounding them to bf16 before the normalisation costs the soft-logit test cases their token
+// parity.  gamma | beta arrive through the ring.
 enum { DB_PRO_EMBED = 0, DB_PRO_LL = 1 };
-constexpr int DB_LPR = 10;                            // 16-byte items per lane and row (d <= 1280)
-template <int NT, int CW>
+constexpr int DB_G = 5;                               // rows whose loads are in flight together
+constexpr int DB_LPR = 10;                            // 16-byte items per lane and row in the row-per-warp form (d <= 1280)
+template <int NT, int CW, class Dbg>
 __device__ __forceinline__ void db_prologue_ln(const DbSmem& sm, DbRing& ring, const DbArgs& a, int R, int mode, const uint2* __restrict__ x_ll,
-                                               uint32_t epoch, int warp, int lane, DbDbg& dbg) {
+                                               uint32_t epoch, int warp, int lane, Dbg& dbg) {
     using C = DbCfg<NT, CW>;
     const DbModel& M = c_db;
     const int d = M.d, tid = warp * 32 + lane, items = d >> 2, row_words = d >> 1;
-    dbg.smark(0);
+    float* part = sm.red;                                                  // [CW][ROWS][sum, sum of squares]
     csync<C::CONS>();                                                      // the previous stage is done with xs / red
-    dbg.smark(1);
     if (mode == DB_PRO_EMBED) {
         if (!a.x_in) {
             if (tid < R) sm.stok[tid] = a.tokens[db_trow(a, tid) * DEC_TOK_LD + sm.spos[tid / a.nbw]];
             csync<C::CONS>();
         }
-    } else {
-        ll_wait_sentinels<C::CONS>(x_ll, epoch, row_words, 0, row_words, 8, R - 1, R, tid, 12);   // written by 16-column GEMV tiles (8 words)
-    }
-    dbg.smark(2);
-    db_wait(&sm.full[ring.slot], ring.phase);                              // gamma | beta: one slot ahead of the stage's tiles
-    dbg.smark(3);
-    const float4* gsl = reinterpret_cast<const float4*>(sm.ring + (size_t)ring.slot * DB_SLOT);
-    const float inv_d = __fdividef(1.f, (float)d);       // (an IEEE division would bring a slow-path subroutine: see db_timeout)
-    if (mode == DB_PRO_EMBED) {
-        // opens every step (nothing hides it): one row per round, the row's fp32 sums stay in registers
+        db_wait(&sm.full[ring.slot], ring.phase);                          // gamma | beta: one slot ahead of the stage's tiles
+        const float4* gsl = reinterpret_cast<const float4*>(sm.ring + (size_t)ring.slot * DB_SLOT);
+        const float inv_d = __fdividef(1.f, (float)d);
 #pragma unroll 1
         for (int r = warp; r < R; r += CW) {
             float x[DB_LPR][4];
@@ -439,72 +425,110 @@ __device__ __forceinline__ void db_prologue_ln(const DbSmem& sm, DbRing& ring, c
                 }
             }
         }
-    } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[ring.slot]);
+        ring.advance();
+        csync<C::CONS>();
+        return;
+    }
+    bool v[C::IPR];
+    int cc[C::IPR];
+#pragma unroll
+    for (int i = 0; i < C::IPR; ++i) { v[i] = tid + i * C::CONS < items; cc[i] = v[i] ? tid + i * C::CONS : 0; }   // out of range: re-read item 0
+    {
+        ll_wait_sentinels<C::CONS>(x_ll, epoch, row_words, 0, row_words, 8, R - 1, R, tid, 12);   // written by 16-column GEMV tiles (8 words)
 #pragma unroll 1
-        for (int r0 = warp; r0 < R; r0 += 2 * CW) {
-            const int r1 = r0 + CW < R ? r0 + CW : r0;                     // a warp without a second row repeats its first
-            uint32_t px[2][DB_LPR][2];                                     // the bf16x2 payloads of the two rows
-            {
-                const uint2* p0 = x_ll + (long)r0 * row_words;
-                const uint2* p1 = x_ll + (long)r1 * row_words;
-                u64 w[2][DB_LPR][2];                                       // all 20 loads are issued before the first epoch is looked at
-                unsigned spins = 0;
-                bool ok;
-                do {
+        for (int r0 = 0; r0 < R; r0 += DB_G) {
+            u64 w[DB_G][C::IPR][2];
+            const uint2* pr[DB_G];
 #pragma unroll
-                    for (int i = 0; i < DB_LPR; ++i) {
-                        const int c = lane + 32 * i < items ? lane + 32 * i : 0;    // past the row: re-read item 0
-                        ll_ld2(p0 + 2 * c, w[0][i][0], w[0][i][1]); ll_ld2(p1 + 2 * c, w[1][i][0], w[1][i][1]);
-                    }
-                    ok = true;
+            for (int q = 0; q < DB_G; ++q) pr[q] = x_ll + (long)min(r0 + q, R - 1) * row_words;      // rows past R re-read the last row
+            unsigned spins = 0;
+            bool ok;
+            do {
 #pragma unroll
-                    for (int i = 0; i < DB_LPR; ++i) ok = ok & ll_good(w[0][i][0], epoch) & ll_good(w[0][i][1], epoch) & ll_good(w[1][i][0], epoch) & ll_good(w[1][i][1], epoch);
-                    if (!ok) ll_pause(spins, 2);
-                } while (!ok);
-                dbg.smark(4 + 2 * ((r0 - warp) / (2 * CW)));
+                for (int q = 0; q < DB_G; ++q)
 #pragma unroll
-                for (int i = 0; i < DB_LPR; ++i) {
-                    px[0][i][0] = (uint32_t)w[0][i][0]; px[0][i][1] = (uint32_t)w[0][i][1]; px[1][i][0] = (uint32_t)w[1][i][0]; px[1][i][1] = (uint32_t)w[1][i][1];
-                }
-            }
-            float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+                    for (int i = 0; i < C::IPR; ++i) ll_ld2(pr[q] + 2 * cc[i], w[q][i][0], w[q][i][1]);
+                ok = true;
 #pragma unroll
-            for (int q = 0; q < 2; ++q)
+                for (int q = 0; q < DB_G; ++q)
 #pragma unroll
-                for (int i = 0; i < DB_LPR; ++i)
-                    if (lane + 32 * i < items) {
-                        const float x0 = bf16lo(px[q][i][0]), x1 = bf16hi(px[q][i][0]), x2 = bf16lo(px[q][i][1]), x3 = bf16hi(px[q][i][1]);
+                    for (int i = 0; i < C::IPR; ++i) ok = ok & ll_good(w[q][i][0], epoch) & ll_good(w[q][i][1], epoch);
+                if (!ok) ll_pause(spins, 2);
+            } while (!ok);
+            float s1[DB_G], s2[DB_G];
+#pragma unroll
+            for (int q = 0; q < DB_G; ++q) {
+                uint2* dst = reinterpret_cast<uint2*>(sm.xs + (long)min(r0 + q, R - 1) * sm.ldx);
+                s1[q] = 0.f; s2[q] = 0.f;
+#pragma unroll
+                for (int i = 0; i < C::IPR; ++i)
+                    if (v[i]) {
+                        const uint32_t p0 = (uint32_t)w[q][i][0], p1 = (uint32_t)w[q][i][1];
+                        dst[cc[i]] = make_uint2(p0, p1);
+                        const float x0 = bf16lo(p0), x1 = bf16hi(p0), x2 = bf16lo(p1), x3 = bf16hi(p1);
                         s1[q] += (x0 + x1) + (x2 + x3);
                         s2[q] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, s2[q]))));
                     }
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                for (int q = 0; q < 2; ++q) { s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o); s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], o); }
+                for (int q = 0; q < DB_G; ++q) { s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o); s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], o); }
+            if (lane == 0) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                if (q == 1 && r1 == r0) break;                             // (warp uniform)
-                const float mean = s1[q] * inv_d, rstd = rsqrtf(fmaxf(s2[q] * inv_d - mean * mean, 0.f) + 1e-5f);
-                uint2* row = reinterpret_cast<uint2*>(sm.xs + (long)(q ? r1 : r0) * sm.ldx);
-#pragma unroll
-                for (int i = 0; i < DB_LPR; ++i) {
-                    const int c = lane + 32 * i;
-                    if (c < items) {
-                        const float4 ga = gsl[c], be = gsl[items + c];
-                        row[c] = make_uint2(pack_bf16((bf16lo(px[q][i][0]) - mean) * rstd * ga.x + be.x, (bf16hi(px[q][i][0]) - mean) * rstd * ga.y + be.y),
-                                            pack_bf16((bf16lo(px[q][i][1]) - mean) * rstd * ga.z + be.z, (bf16hi(px[q][i][1]) - mean) * rstd * ga.w + be.w));
-                    }
-                }
+                for (int q = 0; q < DB_G; ++q)
+                    if (r0 + q < R) *reinterpret_cast<float2*>(part + (warp * C::ROWS + r0 + q) * 2) = make_float2(s1[q], s2[q]);
             }
-            dbg.smark(5 + 2 * ((r0 - warp) / (2 * CW)));
         }
     }
-    dbg.smark(18);
+    csync<C::CONS>();
+    if (tid < R) {                                                         // one thread per row: (mean, rstd)
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < CW; ++w) { const float2 p = *reinterpret_cast<const float2*>(part + (w * C::ROWS + tid) * 2); s1 += p.x; s2 += p.y; }
+        const float inv_d = __fdividef(1.f, (float)d), mean = s1 * inv_d;
+        *reinterpret_cast<float2*>(sm.rowstat + 2 * tid) = make_float2(mean, rsqrtf(fmaxf(s2 * inv_d - mean * mean, 0.f) + 1e-5f));
+    }
+    db_wait(&sm.full[ring.slot], ring.phase);                              // gamma | beta: one slot ahead of the stage's tiles
+    csync<C::CONS>();
+    {
+        float4 ga[C::IPR], be[C::IPR];
+        const float4* gsl = reinterpret_cast<const float4*>(sm.ring + (size_t)ring.slot * DB_SLOT);
+#pragma unroll
+        for (int i = 0; i < C::IPR; ++i) { ga[i] = gsl[cc[i]]; be[i] = gsl[items + cc[i]]; }
+#pragma unroll 1
+        for (int r0 = 0; r0 < R; r0 += DB_G) {
+            uint2 xv[DB_G][C::IPR];
+            float2 ms[DB_G];
+#pragma unroll
+            for (int q = 0; q < DB_G; ++q) {
+                const int r = min(r0 + q, R - 1);
+                const uint2* row = reinterpret_cast<const uint2*>(sm.xs + (long)r * sm.ldx);
+#pragma unroll
+                for (int i = 0; i < C::IPR; ++i) xv[q][i] = row[cc[i]];
+                ms[q] = *reinterpret_cast<const float2*>(sm.rowstat + 2 * r);
+            }
+#pragma unroll
+            for (int q = 0; q < DB_G; ++q) {
+                if (r0 + q < R) {
+                    uint2* row = reinterpret_cast<uint2*>(sm.xs + (long)(r0 + q) * sm.ldx);
+#pragma unroll
+                    for (int i = 0; i < C::IPR; ++i)
+                        if (v[i]) {
+                            const float mean = ms[q].x, rstd = ms[q].y;
+                            row[cc[i]] = make_uint2(pack_bf16((bf16lo(xv[q][i].x) - mean) * rstd * ga[i].x + be[i].x, (bf16hi(xv[q][i].x) - mean) * rstd * ga[i].y + be[i].y),
+                                                    pack_bf16((bf16lo(xv[q][i].y) - mean) * rstd * ga[i].z + be[i].z, (bf16hi(xv[q][i].y) - mean) * rstd * ga[i].w + be[i].w));
+                        }
+                }
+            }
+        }
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[ring.slot]);
     ring.advance();
     csync<C::CONS>();
-    dbg.smark(19);
 }
 
 // ---- self-attention of the new token, unit = (row, head) ------------------------------------------------------------------
@@ -840,7 +864,7 @@ __device__ __forceinline__ void db_producer(const DbArgs& a, uint8_t* raw) {
 }
 
 // ---- consumers: the stage loop ------------------------------------------------------------------------------------------
-template <int NT, int CW>
+template <int NT, int CW, bool DBG>
 __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsigned seq, int warp, int lane) {
     using C = DbCfg<NT, CW>;
     const DbModel& M = c_db;
@@ -850,12 +874,34 @@ __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsig
     const int n_stages = M.Ld * 8 + (a.no_vocab ? 0 : 1);
     DbRing ring{0, 0, a.n_slots};
     int red_buf = 0;
-    DbDbg dbg{a.dbg + (size_t)cta * DB_DBG_LD, a.dbg != nullptr && tid == 0, -1};
+    DbDbgT<DBG> dbg{a.dbg + (size_t)cta * DB_DBG_LD, a.dbg != nullptr && tid == 0, -1};
     dbg.mark(0);
 
     for (int it = 0; it < n_stages; ++it) {
         const int l = it >> 3, st = it == M.Ld * 8 ? DBS_VOCAB : (it & 7);
         const uint32_t ep = seq * 64u + (uint32_t)l + 1u, ep_prev = ep - 1u;      // ep_prev: x3 of the layer below
+        if (st == DBS_QKV && l < M.Ld) {
+            // Hide DRAM latency: the layer's bias vectors (read by every tile's epilogue) and the cached K / V rows of the
+            // self-attention units this CTA will run two stages from now were last touched a step (360 MB of traffic) ago, so
+            // they come from HBM; an L2 prefetch now makes them L2 hits (~0.2 us instead of > 1 us on the critical path).
+            const DbLayer& L = M.layers[l];
+            const float* const* bv = &L.qkv_b;
+            for (int i = tid; i < 6 * (4 * d / 32); i += C::CONS) {       // 128-byte lines of the six bias vectors (the longest has 4d floats)
+                const int v = i / (4 * d / 32), line = i - v * (4 * d / 32);
+                const int n = v == 0 ? 3 * d : v == 4 ? 4 * d : d;
+                if (line * 32 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(bv[v] + line * 32));
+            }
+            const int H = M.H;
+            for (int u = (cta + db_stage_rot(DBS_SA, nctas)) % nctas; u < R * H; u += nctas) {
+                const int r = u / H, h = u - r * H, trow = db_trow(a, r), pos = sm.spos[r / a.nbw];
+                const int* tab = a.table + trow * 448;
+                for (int j = tid; j < 2 * pos; j += C::CONS) {            // one 128-byte line per (K | V, position)
+                    const int jj = j >> 1;
+                    const bf16* base = a.mkv + (long)(2 * l + (j & 1)) * a.kv_stride;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((long)tab[jj] * 448 + jj) * d + h * 64));
+                }
+            }
+        }
         if (st == DBS_SA) {
             dbg.mark(2 * it + 1);
             db_stage_self_attn<NT, CW>(sm, a, R, a.mkv + (long)(2 * l) * a.kv_stride, a.mkv + (long)(2 * l + 1) * a.kv_stride, ep, cta, nctas,
@@ -869,7 +915,7 @@ __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsig
             dbg.mark(2 * it + 2);
             continue;
         }
-        dbg.sub = it == a.dbg_stage ? it : -1;
+        dbg.set_sub(it == a.dbg_stage ? it : -1);
         {   // prologue first, with as little live state as possible (the stage descriptor is built after it)
             const DbStageDesc sd = db_stage_desc(st, l < M.Ld ? l : 0, cta, nctas);
             int u0, u1;
@@ -886,8 +932,7 @@ __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsig
                     dbg.smark(1);
                     ll_wait_sentinels<C::CONS>(src, ep, d >> 1, 0, d >> 1, 32, 0, R, tid, 13);
                     dbg.smark(2);
-                    if (a.copy_u == 4) ll_copy_region<C::CONS, 4>(src, ep, R, d >> 1, 0, d >> 2, sm.xs, sm.ldx, tid, 3, &dbg);
-                    else ll_copy_region<C::CONS, 13>(src, ep, R, d >> 1, 0, d >> 2, sm.xs, sm.ldx, tid, 3, &dbg);
+                    ll_copy_region<C::CONS>(src, ep, R, d >> 1, 0, d >> 2, sm.xs, sm.ldx, tid, 3);
                     dbg.smark(3);
                     csync<C::CONS>();
                     dbg.smark(4);
@@ -909,7 +954,7 @@ __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsig
 
 // The role split comes first: whatever is live across setmaxnreg must fit the smaller register file, so each role derives its
 // own state afterwards.
-template <int NT, int CW>
+template <int NT, int CW, bool DBG>
 __global__ void __launch_bounds__(DbCfg<NT, CW>::THREADS, 1) decoder_batch_kernel(const __grid_constant__ DbArgs a) {
     using C = DbCfg<NT, CW>;
     extern __shared__ __align__(128) uint8_t db_raw[];
@@ -935,14 +980,14 @@ __global__ void __launch_bounds__(DbCfg<NT, CW>::THREADS, 1) decoder_batch_kerne
     if (tid < a.W) db_smem<NT, CW>(a, db_raw).spos[tid] = min(a.st ? a.st[tid].pos : a.text_offset, N_TEXT_CTX - 1);
     const unsigned seq = a.barrier[2];                 // written by the previous launch
     __syncthreads();
-    db_consumer<NT, CW>(a, db_raw, seq, tid >> 5, tid & 31);
+    db_consumer<NT, CW, DBG>(a, db_raw, seq, tid >> 5, tid & 31);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------
 void db_set_model(const DbModel& m) { B200_CHECK(cudaMemcpyToSymbol(c_db, &m, sizeof(DbModel))); }
 
 int db_consumer_warps() {
-    static const int cw = [] { const char* e = getenv("B200_STEP_WARPS"); const int v = e ? atoi(e) : 7; return v == 4 ? 4 : (v == 8 ? 8 : 7); }();
+    static const int cw = [] { const char* e = getenv("B200_STEP_WARPS"); const int v = e ? atoi(e) : 7; return v == 8 ? 8 : 7; }();
     return cw;
 }
 
@@ -984,10 +1029,10 @@ void db_carve_ll(DbArgs& a, uint2* p, size_t d, size_t H) {
     a.ll_x1b = p; p += R * d / 2; a.ll_x2b = p; p += R * d / 2; a.ll_x3b = p;
 }
 
-template <int NT, int CW>
+template <int NT, int CW, bool DBG>
 static bool db_launch_t(const DbArgs& a, int n_ctas, size_t smem, cudaStream_t s) {
     static size_t attr = 0;
-    auto* kern = decoder_batch_kernel<NT, CW>;
+    auto* kern = decoder_batch_kernel<NT, CW, DBG>;
     if (smem > attr) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             cudaGetLastError();
@@ -1008,8 +1053,11 @@ static bool db_launch_t(const DbArgs& a, int n_ctas, size_t smem, cudaStream_t s
 bool db_launch(const DbArgs& a, int n_ctas, cudaStream_t s) {
     const int rows = a.W * a.nbw, nt = (rows + 7) / 8, cw = db_consumer_warps();
     const size_t smem = (size_t)a.ring_offset + (size_t)a.n_slots * DB_SLOT;
+    // the stage-timeline marks are a separate instantiation (tools/step_timeline.py): the production kernel carries none
 #define DB_CASE(NT_)                                                                                                   \
-    case NT_: return cw == 4 ? db_launch_t<NT_, 4>(a, n_ctas, smem, s) : cw == 8 ? db_launch_t<NT_, 8>(a, n_ctas, smem, s) : db_launch_t<NT_, 7>(a, n_ctas, smem, s);
+    case NT_:                                                                                                          \
+        if (a.dbg) return db_launch_t<NT_, 7, true>(a, n_ctas, smem, s);                                               \
+        return cw == 8 ? db_launch_t<NT_, 8, false>(a, n_ctas, smem, s) : db_launch_t<NT_, 7, false>(a, n_ctas, smem, s);
     switch (nt) {
         DB_CASE(1) DB_CASE(2) DB_CASE(3) DB_CASE(4) DB_CASE(5)
     default: record_error("decoder_batch: %d rows", rows); return false;
