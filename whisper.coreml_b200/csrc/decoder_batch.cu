@@ -41,19 +41,22 @@ constexpr unsigned DB_SPIN_LIMIT = 1u << 22;
 
 template <int NT, int CW>
 struct DbCfg {
-    // 8 consumer warps: two consumer warpgroups + one producer warpgroup (one active thread); setmaxnreg hands the producer
-    // group's registers to the consumers (384 threads start with 168 registers each: 128 x 56 + 256 x 224 = 64512)
-    static constexpr int PW = CW == 8 ? 4 : 1;                         // producer warps (warp 0 lane 0 does the work)
-    static constexpr bool SETREG = CW == 8;
+    // 8 consumer warps = two TILE GROUPS of four (a GEMV tile is multiplied, reduced and stored by one group while the other
+    // works on the next tile: two dependent chains in flight instead of one), plus one producer warpgroup (one active
+    // thread); setmaxnreg hands the producer group's registers to the consumers
+    static_assert(CW == 8, "two tile groups of four warps");
+    static constexpr int PW = 4;                                       // producer warps (warp 0 lane 0 does the work)
+    static constexpr bool SETREG = true;
     static constexpr int CONS = CW * 32, THREADS = CONS + PW * 32, ROWS = NT * 8;
+    static constexpr int GW = 4, GT = GW * 32;                         // warps / threads of a tile group
+    static constexpr int ARRIVALS = 4;                                 // warps that release a ring slot
     static constexpr int IPR = (320 + CONS - 1) / CONS;               // 16-byte items (4 columns) per row and thread, d <= 1280
-    static constexpr int PASSES = (ROWS * 16 + CONS - 1) / CONS;      // epilogue passes: one (row, output) per thread and pass
-    static constexpr int RED_BUFS = NT <= 2 ? 2 : 1;
-    static constexpr int RED_FLOATS = RED_BUFS * CW * NT * 128;
+    static constexpr int PASSES = (ROWS * 16 + GT - 1) / GT;          // epilogue passes: one (row, output) per group thread and pass
+    static constexpr int RED_FLOATS = 2 * GW * NT * 128;              // one reduction buffer per tile group
 };
 // scratch behind the activation rows, in floats: red | sp | sq | stat | rowstat | ints (spos[8] stok[40]) | barriers
 __host__ __device__ constexpr size_t db_scratch_bytes(int nt, int cw) {
-    return ((size_t)(nt <= 2 ? 2 : 1) * cw * nt * 128 + 8 * DB_SPLIT_KEYS + 8 * 64 + 64 + 2 * DB_MAX_ROWS + 48) * 4 + 2 * DB_MAX_SLOTS * 8;
+    return ((size_t)2 * 4 * nt * 128 + 8 * DB_SPLIT_KEYS + 8 * 64 + 64 + 2 * DB_MAX_ROWS + 48) * 4 + 2 * DB_MAX_SLOTS * 8 + 2 * 64;
 }
 
 __device__ __forceinline__ void db_mma(float (&d)[4], const uint4& lo, const uint4& hi, const uint4& xb) {
@@ -186,9 +189,16 @@ __device__ __forceinline__ int db_slot_blocks(int c0, int n_kc, int chunk_kc) {
     const int chunk_end = min(n_kc, (c0 / chunk_kc + 1) * chunk_kc);
     return min(DB_SLOT_BLOCKS, chunk_end - c0);
 }
+// what a GEMV tile's epilogue needs to know about its stage: filled by ONE thread per stage (the look-ups are chains of selects
+// over the stage kind; evaluated per tile they were most of the epilogue's instructions), read by everybody from shared memory
+static_assert(true, "");
+struct DbStageSm {
+    const float* bias; const uint2* res_ll; uint2* out_ll; uint2* out_llb; long ld_out;
+    int n_valid, epi, res_mode; uint32_t res_epoch;
+};
 struct DbSmem {
     uint8_t* ring; bf16* xs; float* red; float* sp; float* sq; float* stat; float* rowstat; int* spos; int* stok;
-    uint64_t* full; uint64_t* empty;
+    uint64_t* full; uint64_t* empty; DbStageSm* desc;
     int ldx;
 };
 // row r of the step -> index of its token history / slot-table row / physical KV slot
@@ -229,30 +239,38 @@ struct DbGemv {
     __device__ __forceinline__ int n_valid() const { return st == DBS_QKV ? 3 * c_db.d : st == DBS_M1 ? 4 * c_db.d : st == DBS_VOCAB ? c_db.V : c_db.d; }
 };
 
+template <int CONS>
+__device__ __forceinline__ void gsync(int group) { asm volatile("bar.sync %0, %1;" ::"r"(2 + group), "n"(CONS) : "memory"); }
+
 template <int NT, int CW, class Dbg>
-__device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, int& red_buf, const DbGemv& g, const DbArgs& a, int R,
+__device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, const DbGemv& g, const DbStageSm& D, const DbArgs& a, int R,
                                               int nctas, int warp, int lane, Dbg& dbg) {
     using C = DbCfg<NT, CW>;
     const DbModel& M = c_db;
     const int gq = lane >> 2, tq = lane & 3, tid = warp * 32 + lane;
+    const int group = warp >> 2, gw = warp & 3, gtid = tid & (C::GT - 1);
     const bf16* xrow = sm.xs + (long)gq * sm.ldx + tq * 8;
+    const bool chunked = g.chunk_kc < g.n_kc;          // MLP2 with the hidden row staged in K chunks: one group owns every tile
     int u0, u1;
     db_range(g.n_tiles, g.vcta, nctas, u0, u1);
     for (int t = u0; t < u1; ++t) {
+        const bool mine = chunked ? group == 0 : ((t - u0) & 1) == group;          // (uniform within a group)
         float add[C::PASSES];
+        if (mine) {
 #pragma unroll
-        for (int p = 0; p < C::PASSES; ++p) {
-            const int idx = tid + p * C::CONS, r = idx >> 4, n = t * 16 + (idx & 15);
-            add[p] = 0.f;
-            if (r < R && n < g.n_valid()) {
-                const float* bias = g.bias();
-                const int res_mode = g.res_mode(a);
-                if (bias) add[p] = __ldg(bias + n);
-                if (res_mode == DB_RES_LL) add[p] += __uint_as_float(ll_wait_word(g.res_ll(a) + (long)r * M.d + n, g.res_epoch(), 1));
-                else if (res_mode == DB_RES_EMBED) {
-                    const int pos = sm.spos[r / a.nbw];
-                    add[p] += __bfloat162float(M.tok_emb[(long)a.tokens[db_trow(a, r) * DEC_TOK_LD + pos] * M.d + n]) + __ldg(M.pos_emb + (long)pos * M.d + n);
-                } else if (res_mode == DB_RES_XIN) add[p] += __ldg(a.x_in + (long)r * M.d + n);
+            for (int p = 0; p < C::PASSES; ++p) {
+                const int idx = gtid + p * C::GT, r = idx >> 4, n = t * 16 + (idx & 15);
+                add[p] = 0.f;
+                if (r < R && n < D.n_valid) {
+                    const float* bias = D.bias;
+                    const int res_mode = D.res_mode;
+                    if (bias) add[p] = __ldg(bias + n);
+                    if (res_mode == DB_RES_LL) add[p] += __uint_as_float(ll_wait_word(D.res_ll + (long)r * M.d + n, D.res_epoch, 1));
+                    else if (res_mode == DB_RES_EMBED) {
+                        const int pos = sm.spos[r / a.nbw];
+                        add[p] += __bfloat162float(M.tok_emb[(long)a.tokens[db_trow(a, r) * DEC_TOK_LD + pos] * M.d + n]) + __ldg(M.pos_emb + (long)pos * M.d + n);
+                    } else if (res_mode == DB_RES_XIN) add[p] += __ldg(a.x_in + (long)r * M.d + n);
+                }
             }
         }
         dbg.smark(20 + 4 * (t - u0));
@@ -262,83 +280,81 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, in
 #pragma unroll
             for (int e = 0; e < 4; ++e) { acc[j][0][e] = 0.f; acc[j][1][e] = 0.f; }
         for (int c0 = 0, nblk = 0; c0 < g.n_kc; c0 += nblk) {
-            const int cin = c0 % g.chunk_kc;                            // first block of the slot within the staged columns
-            nblk = db_slot_blocks(c0, g.n_kc, g.chunk_kc);
-            if (g.st == DBS_M2 && cin == 0 && !(g.chunk_kc >= g.n_kc && t > u0)) {   // a new K chunk of the MLP hidden row (one chunk: staged once)
+            // first block of the slot within the staged columns, blocks of the slot (no divisions on the common path)
+            const int cin = chunked ? c0 % g.chunk_kc : c0;
+            nblk = chunked ? db_slot_blocks(c0, g.n_kc, g.chunk_kc) : min(DB_SLOT_BLOCKS, g.n_kc - c0);
+            if (g.st == DBS_M2 && cin == 0 && !(!chunked && t > u0)) {  // a new K chunk of the MLP hidden row (one chunk: staged once)
                 csync<C::CONS>();                                       // everybody is done with the previous chunk
                 const int word0 = c0 * 16, n_words = min(g.chunk_kc, g.n_kc - c0) * 16;
                 ll_wait_sentinels<C::CONS>(a.ll_hid, g.ep, 2L * M.d, word0, n_words, 8, R - 1, R, tid, 13);
                 ll_copy_region<C::CONS>(a.ll_hid, g.ep, R, 2L * M.d, word0, n_words / 2, sm.xs, sm.ldx, tid, 3);
                 csync<C::CONS>();
             }
-            const uint4* sl = reinterpret_cast<const uint4*>(sm.ring + (size_t)ring.slot * DB_SLOT) + lane;
-            const bf16* xk = xrow + cin * 32;
-            db_wait(&sm.full[ring.slot], ring.phase);
-            constexpr int BPW = (DB_SLOT_BLOCKS + CW - 1) / CW, QB = BPW <= 6 ? BPW : 5;      // blocks per warp and slot; per batch
+            if (mine) {
+                const uint4* sl = reinterpret_cast<const uint4*>(sm.ring + (size_t)ring.slot * DB_SLOT) + lane;
+                const bf16* xk = xrow + cin * 32;
+                db_wait(&sm.full[ring.slot], ring.phase);
 #pragma unroll
-            for (int q0 = 0; q0 < BPW; q0 += QB) {
-                uint4 lo[QB], hi[QB];
+                for (int q0 = 0; q0 < DB_SLOT_BLOCKS / C::GW; q0 += 5) {           // two batches of five blocks per warp
+                    uint4 lo[5], hi[5];
 #pragma unroll
-                for (int q = 0; q < QB; ++q) {
-                    const int blk = warp + CW * (q0 + q);
-                    if (blk < nblk) { lo[q] = sl[blk * 64]; hi[q] = sl[blk * 64 + 32]; }
-                }
+                    for (int q = 0; q < 5; ++q) {
+                        const int blk = gw + C::GW * (q0 + q);
+                        if (blk < nblk) { lo[q] = sl[blk * 64]; hi[q] = sl[blk * 64 + 32]; }
+                    }
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    if (NT <= 2) {                                      // activation fragments fetched ahead of their MMAs (register budget)
-                        uint4 xb[QB];
+                    for (int j = 0; j < NT; ++j) {
+                        if (NT <= 2) {                                  // activation fragments fetched ahead of their MMAs (register budget)
+                            uint4 xb[5];
 #pragma unroll
-                        for (int q = 0; q < QB; ++q) {
-                            const int blk = warp + CW * (q0 + q);
-                            if (blk < nblk) xb[q] = *reinterpret_cast<const uint4*>(xk + (long)j * 8 * sm.ldx + blk * 32);
-                        }
+                            for (int q = 0; q < 5; ++q) {
+                                const int blk = gw + C::GW * (q0 + q);
+                                if (blk < nblk) xb[q] = *reinterpret_cast<const uint4*>(xk + (long)j * 8 * sm.ldx + blk * 32);
+                            }
 #pragma unroll
-                        for (int q = 0; q < QB; ++q)
-                            if (warp + CW * (q0 + q) < nblk) db_mma(acc[j][q & 1], lo[q], hi[q], xb[q]);
-                    } else {
+                            for (int q = 0; q < 5; ++q)
+                                if (gw + C::GW * (q0 + q) < nblk) db_mma(acc[j][q & 1], lo[q], hi[q], xb[q]);
+                        } else {
 #pragma unroll
-                        for (int q = 0; q < QB; ++q) {
-                            const int blk = warp + CW * (q0 + q);
-                            if (blk < nblk) db_mma(acc[j][q & 1], lo[q], hi[q], *reinterpret_cast<const uint4*>(xk + (long)j * 8 * sm.ldx + blk * 32));
+                            for (int q = 0; q < 5; ++q) {
+                                const int blk = gw + C::GW * (q0 + q);
+                                if (blk < nblk) db_mma(acc[j][q & 1], lo[q], hi[q], *reinterpret_cast<const uint4*>(xk + (long)j * 8 * sm.ldx + blk * 32));
+                            }
                         }
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[ring.slot]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[ring.slot]);
-            ring.advance();
+            ring.advance();                                             // both groups track every slot of the CTA
         }
+        if (!mine) continue;
         dbg.smark(21 + 4 * (t - u0));
-        float* rw = sm.red + red_buf * (CW * NT * 128) + warp * (NT * 128);
+        float* red = sm.red + group * (C::GW * NT * 128);
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-            float* r = rw + j * 128;
+            float* r = red + gw * (NT * 128) + j * 128;
             r[gq * 8 + tq * 2] = acc[j][0][0] + acc[j][1][0]; r[gq * 8 + tq * 2 + 1] = acc[j][0][1] + acc[j][1][1];
             r[(gq + 8) * 8 + tq * 2] = acc[j][0][2] + acc[j][1][2]; r[(gq + 8) * 8 + tq * 2 + 1] = acc[j][0][3] + acc[j][1][3];
         }
-        csync<C::CONS>();
+        gsync<C::GT>(group);
         dbg.smark(22 + 4 * (t - u0));
 #pragma unroll
         for (int p = 0; p < C::PASSES; ++p) {
-            const int idx = tid + p * C::CONS, r = idx >> 4, o = idx & 15, n = t * 16 + o;
-            const bool owner = r < R && n < g.n_valid();
-            const long ld_out = g.ld_out(a);
-            const int epi = g.epi();
-            const float* rr = sm.red + red_buf * (CW * NT * 128) + (r >> 3) * 128 + o * 8 + (r & 7);
+            const int idx = gtid + p * C::GT, r = idx >> 4, o = idx & 15, n = t * 16 + o;
+            const bool owner = r < R && n < D.n_valid;
+            const long ld_out = D.ld_out;
+            const int epi = D.epi;
+            const float* rr = red + (r >> 3) * 128 + o * 8 + (r & 7);
             float v = add[p];
-            if (idx < C::ROWS * 16) {
-                float s = 0.f;
-#pragma unroll
-                for (int w = 0; w < CW; ++w) s += rr[w * (NT * 128)];
-                v += s;
-            }
+            if (idx < C::ROWS * 16) v += (rr[0] + rr[NT * 128]) + (rr[2 * NT * 128] + rr[3 * NT * 128]);
             if (epi == DB_EPI_LL_GELU_BF16) {
                 v = gelu_erf(v);
                 const float nxt = __shfl_down_sync(0xffffffffu, v, 1);          // lanes are (row, o): o + 1 is the next lane
-                if (owner && !(o & 1)) ll_st(g.out_ll(a) + ((long)r * ld_out + n) / 2, pack_bf16(v, nxt), g.ep);
+                if (owner && !(o & 1)) ll_st(D.out_ll + ((long)r * ld_out + n) / 2, pack_bf16(v, nxt), g.ep);
             } else if (epi == DB_EPI_LL_F32) {
-                if (owner) ll_st(g.out_ll(a) + (long)r * ld_out + n, __float_as_uint(v), g.ep);
-                uint2* out_llb = g.out_llb(a);
+                if (owner) ll_st(D.out_ll + (long)r * ld_out + n, __float_as_uint(v), g.ep);
+                uint2* out_llb = D.out_llb;
                 if (out_llb) {                                        // (stage uniform)
                     const float nxt = __shfl_down_sync(0xffffffffu, v, 1);
                     if (owner && !(o & 1)) ll_st(out_llb + ((long)r * ld_out + n) / 2, pack_bf16(v, nxt), g.ep);
@@ -348,8 +364,7 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, in
             }
         }
         dbg.smark(23 + 4 * (t - u0));
-        if (C::RED_BUFS == 2) red_buf ^= 1;           // the next unit reduces through the other buffer: one barrier per unit
-        else csync<C::CONS>();
+        gsync<C::GT>(group);                            // the group's next tile reuses its reduction buffer
     }
 }
 
@@ -425,10 +440,9 @@ __device__ __forceinline__ void db_prologue_ln(const DbSmem& sm, DbRing& ring, c
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[ring.slot]);
+        csync<C::CONS>();                                                  // every warp is done with gamma | beta
+        if (warp < C::ARRIVALS && lane == 0) mbar_arrive(&sm.empty[ring.slot]);
         ring.advance();
-        csync<C::CONS>();
         return;
     }
     bool v[C::IPR];
@@ -525,10 +539,9 @@ __device__ __forceinline__ void db_prologue_ln(const DbSmem& sm, DbRing& ring, c
             }
         }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty[ring.slot]);
+    csync<C::CONS>();                                                      // every warp is done with gamma | beta
+    if (warp < C::ARRIVALS && lane == 0) mbar_arrive(&sm.empty[ring.slot]);
     ring.advance();
-    csync<C::CONS>();
 }
 
 // ---- self-attention of the new token, unit = (row, head) ------------------------------------------------------------------
@@ -674,10 +687,9 @@ __device__ __forceinline__ void db_stage_cross_attn(const DbSmem& sm, DbRing& ri
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[ring.slot]);
+        csync<C::CONS>();                                                  // every warp has read its key tiles
+        if (warp < C::ARRIVALS && lane == 0) mbar_arrive(&sm.empty[ring.slot]);
         ring.advance();
-        csync<C::CONS>();
         // partial softmax per beam over the split's valid keys; p (bf16) becomes the B operand of P V
         for (int b = warp; b < nbw; b += CW) {
             float sv[DB_SPLIT_KEYS / 32];
@@ -717,7 +729,7 @@ __device__ __forceinline__ void db_stage_cross_attn(const DbSmem& sm, DbRing& ri
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[ring.slot]);
+        if (warp < C::ARRIVALS && lane == 0) mbar_arrive(&sm.empty[ring.slot]);     // (warps 0 - 3 are the ones that read the V^T tiles)
         ring.advance();
         if (tid < nbw) { ll_st(part + tid * 66, __float_as_uint(sm.stat[32 + tid]), ep); ll_st(part + tid * 66 + 1, __float_as_uint(sm.stat[40 + tid]), ep); }
         if (s == DB_N_SPLITS - 1) {
@@ -798,6 +810,7 @@ __device__ __forceinline__ DbSmem db_smem(const DbArgs& a, uint8_t* raw) {
     sm.stok = sm.spos + 8;                             // [40] current token of each row
     sm.full = reinterpret_cast<uint64_t*>(sm.stok + 40);
     sm.empty = sm.full + DB_MAX_SLOTS;
+    sm.desc = reinterpret_cast<DbStageSm*>(sm.empty + DB_MAX_SLOTS);       // [2], 64 bytes each
     sm.ring = raw + a.ring_offset;
     return sm;
 }
@@ -853,7 +866,7 @@ __device__ __forceinline__ void db_producer(const DbArgs& a, uint8_t* raw) {
         for (int t = u0; t < u1; ++t)
 #pragma unroll 1
             for (int c0 = 0, nblk = 0; c0 < sd.n_kc; c0 += nblk) {
-                nblk = db_slot_blocks(c0, sd.n_kc, chunk_kc);
+                nblk = chunk_kc < sd.n_kc ? db_slot_blocks(c0, sd.n_kc, chunk_kc) : min(DB_SLOT_BLOCKS, sd.n_kc - c0);
                 const uint32_t bytes = (uint32_t)nblk * 1024;
                 db_wait(&sm.empty[ring.slot], ring.phase ^ 1);
                 mbar_expect_tx(&sm.full[ring.slot], bytes);
@@ -873,7 +886,6 @@ __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsig
     const DbSmem sm = db_smem<NT, CW>(a, raw);
     const int n_stages = M.Ld * 8 + (a.no_vocab ? 0 : 1);
     DbRing ring{0, 0, a.n_slots};
-    int red_buf = 0;
     DbDbgT<DBG> dbg{a.dbg + (size_t)cta * DB_DBG_LD, a.dbg != nullptr && tid == 0, -1};
     dbg.mark(0);
 
@@ -916,6 +928,13 @@ __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsig
             continue;
         }
         dbg.set_sub(it == a.dbg_stage ? it : -1);
+        DbStageSm& D = sm.desc[it & 1];                // (stage it - 2 is long finished: the prologue barrier of it - 1 lies between)
+        if (tid == 0) {
+            const DbGemv q{st, l < M.Ld ? l : 0, 0, 0, 0, ep, 0};
+            D.bias = q.bias(); D.res_ll = q.res_ll(a); D.out_ll = q.out_ll(a); D.out_llb = q.out_llb(a); D.ld_out = q.ld_out(a);
+            D.n_valid = q.n_valid(); D.epi = q.epi(); D.res_mode = q.res_mode(a); D.res_epoch = q.res_epoch();
+        }
+        if (st == DBS_M2) csync<C::CONS>();            // (the other stages' prologues start with this barrier)
         {   // prologue first, with as little live state as possible (the stage descriptor is built after it)
             const DbStageDesc sd = db_stage_desc(st, l < M.Ld ? l : 0, cta, nctas);
             int u0, u1;
@@ -942,7 +961,7 @@ __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsig
         const DbStageDesc sd = db_stage_desc(st, l < M.Ld ? l : 0, cta, nctas);
         const DbGemv g{st, l < M.Ld ? l : 0, sd.n_tiles, sd.n_kc, sd.vcta, ep, st == DBS_M2 ? min(a.xs_cols >> 5, sd.n_kc) : sd.n_kc};
         dbg.mark(2 * it + 1);
-        db_stage_gemv<NT, CW>(sm, ring, red_buf, g, a, R, nctas, warp, lane, dbg);
+        db_stage_gemv<NT, CW>(sm, ring, g, D, a, R, nctas, warp, lane, dbg);
         dbg.mark(2 * it + 2);
     }
     // the last CTA to leave advances the launch sequence number: by then every CTA has read it
@@ -967,7 +986,7 @@ __global__ void __launch_bounds__(DbCfg<NT, CW>::THREADS, 1) decoder_batch_kerne
         if (C::SETREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (threadIdx.x == 0) {
             uint64_t* full = db_smem<NT, CW>(a, db_raw).full;
-            for (int s = 0; s < DB_MAX_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&full[DB_MAX_SLOTS + s], CW); }
+            for (int s = 0; s < DB_MAX_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&full[DB_MAX_SLOTS + s], C::ARRIVALS); }
             fence_barrier_init();
         }
         __syncthreads();
@@ -987,8 +1006,7 @@ __global__ void __launch_bounds__(DbCfg<NT, CW>::THREADS, 1) decoder_batch_kerne
 void db_set_model(const DbModel& m) { B200_CHECK(cudaMemcpyToSymbol(c_db, &m, sizeof(DbModel))); }
 
 int db_consumer_warps() {
-    static const int cw = [] { const char* e = getenv("B200_STEP_WARPS"); const int v = e ? atoi(e) : 7; return v == 8 ? 8 : 7; }();
-    return cw;
+    return 8;
 }
 
 // Shared-memory plan for `rows` rows: the activation rows hold K chunks of xs_cols columns (>= d: LayerNorm rows are staged
@@ -1051,13 +1069,12 @@ static bool db_launch_t(const DbArgs& a, int n_ctas, size_t smem, cudaStream_t s
 }
 
 bool db_launch(const DbArgs& a, int n_ctas, cudaStream_t s) {
-    const int rows = a.W * a.nbw, nt = (rows + 7) / 8, cw = db_consumer_warps();
+    const int rows = a.W * a.nbw, nt = (rows + 7) / 8;
     const size_t smem = (size_t)a.ring_offset + (size_t)a.n_slots * DB_SLOT;
     // the stage-timeline marks are a separate instantiation (tools/step_timeline.py): the production kernel carries none
 #define DB_CASE(NT_)                                                                                                   \
     case NT_:                                                                                                          \
-        if (a.dbg) return db_launch_t<NT_, 7, true>(a, n_ctas, smem, s);                                               \
-        return cw == 8 ? db_launch_t<NT_, 8, false>(a, n_ctas, smem, s) : db_launch_t<NT_, 7, false>(a, n_ctas, smem, s);
+        return a.dbg ? db_launch_t<NT_, 8, true>(a, n_ctas, smem, s) : db_launch_t<NT_, 8, false>(a, n_ctas, smem, s);
     switch (nt) {
         DB_CASE(1) DB_CASE(2) DB_CASE(3) DB_CASE(4) DB_CASE(5)
     default: record_error("decoder_batch: %d rows", rows); return false;

@@ -50,7 +50,6 @@ struct DbArgs {
     int no_vocab;                        // stop after the last layer (prompt positions whose logits nobody reads)
     unsigned* barrier;                   // [1] CTAs that have left the kernel, [2] launch sequence number
     unsigned long long* dbg;             // optional stage timeline: [n_ctas][DB_DBG_LD] %globaltimer values (0 = not reached)
-    int copy_u;                          // experiment: loads in flight per thread in the activation copies (B200_STEP_COPYU)
     int dbg_stage;                       // stage index whose inner marks are recorded at 600.. (B200_STEP_PROBE), -1 = none
 };
 
