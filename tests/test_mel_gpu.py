@@ -58,8 +58,11 @@ def test_load_audio_wav_stereo_44k(tmp_path):
     path = str(tmp_path / "a.wav")
     with wave.open(path, "wb") as w:
         w.setnchannels(2); w.setsampwidth(2); w.setframerate(44100); w.writeframes(pcm.tobytes())
-    got = load_audio(path).cpu().numpy()
+    got = load_audio(path, quantize_s16=False).cpu().numpy()
     mono = pcm.astype(np.float64).mean(axis=1) / 32768.0
     want = oa.resample_poly(mono, 44100)
     assert got.shape == want.shape == (16000,)
     assert np.abs(got - want).max() < 2e-6
+    # default: rounded to the int16 grid like the reference's `ffmpeg -f s16le` pipe (whisper/audio.py:45-62)
+    q = load_audio(path).cpu().numpy()
+    assert np.abs(q * 32768.0 - np.round(q * 32768.0)).max() < 1e-3 and np.abs(q - want).max() <= 0.5 / 32768.0 + 2e-6

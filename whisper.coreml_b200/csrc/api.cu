@@ -5,8 +5,6 @@
 #include <stdlib.h>
 
 #include "api_batch.cuh"
-#include "decoder_mega.cuh"
-#include "decoder_step.cuh"
 #include "gemm.cuh"
 #include "ops.cuh"
 #include "state.cuh"
@@ -15,7 +13,6 @@
 namespace b200 {
 
 int take_errors(char*, int);
-bool run_step_mega(int nb, int text_offset, const float* d_mask, const float* d_x_in, const MegaArgs* decode_fields);
 void gemm_clear_map_cache();
 void attention_clear_map_cache();
 void decode_clear_graphs();
@@ -205,135 +202,29 @@ void run_prefill(int beam_idx, bool want_chw, int rows) {
 }
 
 // =================================================================================================
-// decoder1 step (whisper/decoder.py:241-257, 261-327; coreml.mm:404-444)
+// decoder1 step (whisper/decoder.py:241-257, 261-327; coreml.mm:404-444): descriptor of the batched persistent step kernel
 // =================================================================================================
-void run_step(int nb, int t, const float* d_mask, bool want_logits, const int* d_t, const int* d_skip) {
-    State& s = S();
-    const int d = s.d;
-    cudaStream_t st = s.stream;
-    for (int l = 0; l < s.Ld; ++l) {
-        const DecLayer& L = s.dec_layers[l];
-        StepGemv g{};
-        g.nb = nb; g.eps = 1e-5f; g.d_skip = d_skip;
-        // LN + fused q|k|v
-        g.w_frag = L.qkv.frag; g.bias = L.qkv.b; g.N = 3 * d; g.K = d; g.x_f32 = s.sx; g.ld_x = d;
-        g.ln_g = L.attn_ln_w; g.ln_b = L.attn_ln_b; g.out_f32 = s.sqkv; g.ld_out = 3L * d;
-        step_gemv(g, st);
-        StepSelfAttn a{};
-        a.qkv = s.sqkv; a.cache_k = s.mk_ptr(l); a.cache_v = s.mv_ptr(l); a.table = s.table; a.mask = d_mask;
-        a.text_offset = t; a.d_text_offset = d_t; a.d_skip = d_skip; a.nb = nb; a.n_head = s.H; a.d = d; a.out = s.satt;
-        step_self_attn(a, st);
-        // out projection + residual (in place)
-        g = StepGemv{}; g.nb = nb; g.d_skip = d_skip;
-        g.w_frag = L.attn_out.frag; g.bias = L.attn_out.b; g.N = d; g.K = d; g.x_bf16 = s.satt; g.ld_x = d;
-        g.residual = s.sx; g.ld_res = d; g.out_f32 = s.sx; g.ld_out = d;
-        step_gemv(g, st);
-        // LN + cross query
-        g = StepGemv{}; g.nb = nb; g.d_skip = d_skip; g.eps = 1e-5f;
-        g.w_frag = L.cross_q.frag; g.bias = L.cross_q.b; g.N = d; g.K = d; g.x_f32 = s.sx; g.ld_x = d;
-        g.ln_g = L.cross_ln_w; g.ln_b = L.cross_ln_b; g.out_f32 = s.sq; g.ld_out = d;
-        step_gemv(g, st);
-        StepCrossAttn c{};
-        c.q = s.sq; c.ck = s.ck_ptr(s.cur_window, l); c.cv = s.cv_ptr(s.cur_window, l); c.nb = nb; c.n_head = s.H;
-        c.d = d; c.n_keys = N_AUDIO_CTX; c.part = s.spart; c.counters = s.scounters; c.out = s.satt; c.d_skip = d_skip;
-        step_cross_attn(c, st);
-        g = StepGemv{}; g.nb = nb; g.d_skip = d_skip;
-        g.w_frag = L.cross_out.frag; g.bias = L.cross_out.b; g.N = d; g.K = d; g.x_bf16 = s.satt; g.ld_x = d;
-        g.residual = s.sx; g.ld_res = d; g.out_f32 = s.sx; g.ld_out = d;
-        step_gemv(g, st);
-        // LN + MLP
-        g = StepGemv{}; g.nb = nb; g.d_skip = d_skip; g.eps = 1e-5f;
-        g.w_frag = L.mlp1.frag; g.bias = L.mlp1.b; g.N = 4 * d; g.K = d; g.x_f32 = s.sx; g.ld_x = d;
-        g.ln_g = L.mlp_ln_w; g.ln_b = L.mlp_ln_b; g.gelu = 1; g.out_bf16 = s.shid; g.ld_out = 4L * d;
-        step_gemv(g, st);
-        g = StepGemv{}; g.nb = nb; g.d_skip = d_skip;
-        g.w_frag = L.mlp2.frag; g.bias = L.mlp2.b; g.N = d; g.K = 4 * d; g.x_bf16 = s.shid; g.ld_x = 4L * d;
-        g.residual = s.sx; g.ld_res = d; g.out_f32 = s.sx; g.ld_out = d;
-        step_gemv(g, st);
-    }
-    if (want_logits) {                                                  // final LN + tied vocabulary projection
-        StepGemv g{};
-        g.nb = nb; g.eps = 1e-5f; g.d_skip = d_skip;
-        g.w_frag = s.tok_emb_frag; g.N = s.V; g.K = d; g.x_f32 = s.sx; g.ld_x = d; g.ln_g = s.ln_w; g.ln_b = s.ln_b;
-        g.out_f32 = s.slogits; g.ld_out = s.V;
-        step_gemv(g, st);
-    }
-}
-
-// =================================================================================================
-// persistent step kernel: model descriptor + launch
-// =================================================================================================
-static void build_mega_model() {
+static void build_step_model() {
     State& s = S();
     if (!s.dec1_loaded || !s.dec256_loaded || !s.mkv) return;
-    if (s.Ld > MEGA_MAX_LAYERS) return;
-    MegaModel m{};
+    if (s.Ld > DB_MAX_LAYERS) return;
+    DbModel m{};
     m.d = s.d; m.H = s.H; m.Ld = s.Ld; m.V = s.V; m.n_tiles_vocab = (s.V + 15) / 16;
     m.tok_emb = s.tok_emb; m.tok_emb_frag = s.tok_emb_frag; m.pos_emb = s.pos_emb; m.ln_w = s.ln_w; m.ln_b = s.ln_b;
     for (int l = 0; l < s.Ld; ++l) {
         const DecLayer& L = s.dec_layers[l];
-        MegaLayer& o = m.layers[l];
+        DbLayer& o = m.layers[l];
         o.qkv = L.qkv.frag; o.attn_out = L.attn_out.frag; o.cross_q = L.cross_q.frag; o.cross_out = L.cross_out.frag;
         o.mlp1 = L.mlp1.frag; o.mlp2 = L.mlp2.frag;
         o.qkv_b = L.qkv.b; o.attn_out_b = L.attn_out.b; o.cross_q_b = L.cross_q.b; o.cross_out_b = L.cross_out.b;
         o.mlp1_b = L.mlp1.b; o.mlp2_b = L.mlp2.b;
         o.ln1_w = L.attn_ln_w; o.ln1_b = L.attn_ln_b; o.ln2_w = L.cross_ln_w; o.ln2_b = L.cross_ln_b; o.ln3_w = L.mlp_ln_w; o.ln3_b = L.mlp_ln_b;
     }
-    if (!s.mega_model && cudaMalloc(&s.mega_model, sizeof(MegaModel)) != cudaSuccess) { cudaGetLastError(); s.mega_model = nullptr; return; }
-    B200_CHECK(cudaMemcpy(s.mega_model, &m, sizeof(MegaModel), cudaMemcpyHostToDevice));
-    mega_set_model(m);
-    static_assert(sizeof(DbLayer) == sizeof(MegaLayer), "same layer descriptor");
-    DbModel b{};
-    b.d = m.d; b.H = m.H; b.Ld = m.Ld; b.V = m.V; b.n_tiles_vocab = m.n_tiles_vocab;
-    b.tok_emb = m.tok_emb; b.tok_emb_frag = m.tok_emb_frag; b.pos_emb = m.pos_emb; b.ln_w = m.ln_w; b.ln_b = m.ln_b;
-    memcpy(b.layers, m.layers, sizeof(DbLayer) * (size_t)s.Ld);
-    batch_set_model(b);
-}
-
-// columns of the bf16 activation rows in shared memory: the MLP hidden row (4d) or the 256 cached K | V rows of a self-attention unit (64 KB)
-static int mega_xs_cols(int d) { return std::max(4 * d, 4096); }
-
-bool mega_available() {
-    State& s = S();
-    if (s.step_impl < 0) {
-        const char* e = getenv("B200_STEP_IMPL");
-        s.step_impl = (e && (!strcmp(e, "v1") || !strcmp(e, "1"))) ? 1 : 0;     // default: the persistent kernel; v1 = one kernel per stage
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&s.n_sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&s.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    }
-    return s.step_impl == 0 && s.mega_model && s.mega_ll && s.d % 64 == 0 && s.d <= 1280 && s.Ld <= MEGA_MAX_LAYERS &&
-           mega_smem_bytes(mega_xs_cols(s.d), STEP_MAX_BEAMS) <= (size_t)s.smem_optin &&
-           mega_smem_bytes(mega_xs_cols(s.d), 5) <= (size_t)s.smem_optin;
-}
-
-// One token step in one launch.  dc == nullptr: reference ABI semantics (x from the host, logits out, no sampling).
-bool run_step_mega(int nb, int text_offset, const float* d_mask, const float* d_x_in, const MegaArgs* decode_fields) {
-    State& s = S();
-    MegaArgs a{};
-    if (decode_fields) a = *decode_fields;
-    a.ckv_frag = s.ckv_frag + (size_t)s.cur_window * s.ckv_frag_window_elems();
-    a.nb = nb; a.xs_cols = mega_xs_cols(s.d); a.xs_rows = mega_xs_rows(nb); a.ring_offset = (int)mega_ring_offset(a.xs_cols, nb);
-    { static const char* e = getenv("B200_MEGA_DELAY"); a.dbg_delay = e ? atoll(e) : 0; }
-    a.n_slots = mega_slots(nb); a.sa_cap = mega_sa_cap(a.xs_cols, nb);
-    { static const char* e = getenv("B200_MEGA_SLOTS"); if (e && atoi(e) >= 2 && atoi(e) < a.n_slots) a.n_slots = atoi(e); }
-    const size_t d = s.d, B = STEP_MAX_BEAMS;
-    uint2* p = s.mega_ll;                                               // carved in the order of mega_ll_words()
-    a.ll_qkv = p; p += B * 3 * d; a.ll_att = p; p += B * d / 2; a.ll_catt = p; p += B * d / 2;
-    a.ll_x1 = p; p += B * d; a.ll_x2 = p; p += B * d; a.ll_x3 = p; p += B * d; a.ll_q = p; p += B * d;
-    a.ll_cap = p; p += (size_t)s.H * 7 * 8 * 66; a.ll_hid = p; p += B * 2 * d;
-    a.ll_x1b = p; p += B * d / 2; a.ll_x2b = p; p += B * d / 2; a.ll_x3b = p;
-    a.logits = s.slogits; a.ld_logits = s.V; a.table = s.table; a.mkv = s.mkv; a.kv_stride = (long)s.bs * N_TEXT_CTX * s.d;
-    a.mask = d_mask; a.x_in = d_x_in; a.text_offset = text_offset; a.barrier = s.mega_barrier; a.seq = s.mega_barrier + 2; a.dbg = s.mega_dbg;
-    static const int force_ctas = getenv("B200_MEGA_CTAS") ? atoi(getenv("B200_MEGA_CTAS")) : 0;      // experiments: fixed grid size
-    return mega_launch(a, force_ctas > 0 ? force_ctas : (s.mega_ctas > 0 ? s.mega_ctas : s.n_sms), s.stream);
-}
-size_t mega_ll_words_for(size_t d, size_t H);
-static size_t mega_ll_words(size_t d, size_t H) { return mega_ll_words_for(d, H); }
-size_t mega_ll_words_for(size_t d, size_t H) {
-    const size_t B = STEP_MAX_BEAMS;
-    return B * 3 * d + 2 * (B * d / 2) + 4 * B * d + H * 7 * 8 * 66 + B * 2 * d + 3 * (B * d / 2);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&s.n_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&s.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    batch_set_model(m);
 }
 
 // =================================================================================================
@@ -504,7 +395,7 @@ void loadDecoder256(const char* modelPath, int n_layer, int n_state, int n_head,
     build_dump_slots();
     if (!ok) return;
     s.dec256_loaded = true;
-    build_mega_model();
+    build_step_model();
 }
 
 void closeDecoder256() {
@@ -512,12 +403,10 @@ void closeDecoder256() {
     if (!s.dec256_loaded) return;
     use_device();
     B200_CHECK(cudaDeviceSynchronize());
-    decode_free_lanes();
     batch_free();
     dev_free(&s.mkv); dev_free(&s.table); dev_free(&s.px); dev_free(&s.pout); dev_free(&s.pmask); dev_free(&s.pchw);
     dev_free(&s.py); dev_free(&s.pqkv); dev_free(&s.patt); dev_free(&s.phid); dev_free(&s.pq); dev_free(&s.d_dump_slot);
     release_decoder_weights();
-    if (s.mega_model) { cudaFree(s.mega_model); s.mega_model = nullptr; }
     s.align_heads.clear();             // a model loaded next starts from the default alignment heads (model.py:55-58), not this one's
     s.dec256_loaded = false;
     gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
@@ -549,17 +438,10 @@ void loadDecoder1(const char* modelPath, int n_layer, int n_state, int n_head, i
     s.d = n_state; s.H = n_state / 64; s.Ld = n_layer;
     const size_t d = s.d, B = STEP_MAX_BEAMS;
     bool ok = true;
-    ok &= dev_alloc(&s.sx, B * d); ok &= dev_alloc(&s.sqkv, B * 3 * d); ok &= dev_alloc(&s.sq, B * d);
-    ok &= dev_alloc(&s.slogits, B * (size_t)s.V); ok &= dev_alloc(&s.smask, (size_t)512);
-    ok &= dev_alloc(&s.spart, (size_t)s.H * 8 * 8 * 66); ok &= dev_alloc(&s.scounters, (size_t)s.H, true);
-    ok &= dev_alloc(&s.satt, B * d); ok &= dev_alloc(&s.shid, B * 4 * d);
-    ok &= dev_alloc(&s.sxin, B * d);
-    ok &= dev_alloc(&s.mega_ll, mega_ll_words(d, s.H), true);
-    ok &= dev_alloc(&s.mega_barrier, (size_t)4, true);
-    if (ok) { const unsigned one = 1; B200_CHECK(cudaMemcpy(s.mega_barrier + 2, &one, sizeof(one), cudaMemcpyHostToDevice)); }   // launch sequence starts at 1: epoch 0 = "never written"
+    ok &= dev_alloc(&s.slogits, B * (size_t)s.V); ok &= dev_alloc(&s.smask, (size_t)512); ok &= dev_alloc(&s.sxin, B * d);
     if (!ok) return;
     s.dec1_loaded = true;
-    build_mega_model();
+    build_step_model();
 }
 
 void closeDecoder1() {
@@ -567,12 +449,8 @@ void closeDecoder1() {
     if (!s.dec1_loaded) return;
     use_device();
     B200_CHECK(cudaDeviceSynchronize());
-    decode_free_lanes();
     batch_free();
-    dev_free(&s.sx); dev_free(&s.sqkv); dev_free(&s.sq); dev_free(&s.slogits); dev_free(&s.smask); dev_free(&s.spart);
-    dev_free(&s.scounters); dev_free(&s.satt); dev_free(&s.shid);
-    dev_free(&s.sxin); dev_free(&s.mega_ll); dev_free(&s.mega_barrier);
-    if (s.mega_model) { cudaFree(s.mega_model); s.mega_model = nullptr; }
+    dev_free(&s.slogits); dev_free(&s.smask); dev_free(&s.sxin);
     decode_clear_graphs();
     release_decoder_weights();
     s.dec1_loaded = false;
@@ -605,12 +483,10 @@ void decoder1Predict(float* x, float* qk_mask, int text_offset, float* out_x) {
     use_device();
     const size_t d = s.d;
     const int nb = s.bs;
-    const bool mega = mega_available();
-    B200_CHECK(cudaMemcpyAsync(mega ? s.sxin : s.sx, x, nb * d * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+    if (!batch_available()) { record_error("decoder1Predict: the step kernel does not support these dimensions (n_state %d, %d layers)", s.d, s.Ld); return; }
+    B200_CHECK(cudaMemcpyAsync(s.sxin, x, nb * d * sizeof(float), cudaMemcpyHostToDevice, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.smask, qk_mask, (size_t)(nb == 1 ? 450 : 449) * sizeof(float), cudaMemcpyHostToDevice, s.stream));
-    if (batch_available()) run_step_batch_abi(nb, text_offset, s.smask, s.sxin);
-    else if (mega) run_step_mega(nb, text_offset, s.smask, s.sxin, nullptr);
-    else run_step(nb, text_offset, s.smask, true, nullptr, nullptr);
+    run_step_batch_abi(nb, text_offset, s.smask, s.sxin);
     B200_CHECK(cudaMemcpyAsync(out_x, s.slogits, (size_t)nb * s.V * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     B200_CHECK(cudaStreamSynchronize(s.stream));
 }

@@ -69,21 +69,9 @@ void batch_free() {
     g_db_model_set = false;
 }
 
-static int step_impl() {                                 // 0 = batched kernel (default), 1 = one-window persistent kernel, 2 = one kernel per stage
-    static const int impl = [] {
-        const char* e = getenv("B200_STEP_IMPL");
-        if (!e) return 0;
-        if (!strcmp(e, "mega")) return 1;
-        if (!strcmp(e, "v1") || !strcmp(e, "1")) return 2;
-        return 0;
-    }();
-    return impl;
-}
-
 bool batch_available() {
     State& s = S();
-    if (step_impl() != 0 || !g_db_model_set || !s.dec1_loaded || !s.dec256_loaded) return false;
-    mega_available();                                    // fills n_sms / smem_optin
+    if (!g_db_model_set || !s.dec1_loaded || !s.dec256_loaded) return false;
     DbGeometry g;
     return s.Ld <= DB_MAX_LAYERS && db_geometry(s.d, 1, s.smem_optin, &g) && db_geometry(s.d, DEC_MAX_BEAMS, s.smem_optin, &g);
 }
@@ -158,6 +146,51 @@ bool run_step_batch_abi(int nb, int text_offset, const float* d_mask, const floa
     a.logits = s.slogits; a.ld_logits = s.V; a.mkv = s.mkv; a.kv_stride = (long)s.bs * N_TEXT_CTX * s.d; a.table = s.table;
     a.mask = d_mask; a.x_in = d_x_in; a.text_offset = text_offset; a.barrier = g_abi_barrier; a.dbg = g_dbg; a.dbg_stage = probe_stage();
     return db_launch(a, grid_ctas(), s.stream);
+}
+
+// decoder1StepFused: the reference ABI's cache (s.mkv / s.table, filled by decoder256Predict / earlier steps), token histories
+// from the caller; the step kernel embeds the last token of every beam, the sampling kernels leave the candidates
+void step_fused_abi(const int* tokens_hist, int n_hist, int sample_begin, int text_offset, int without_timestamps,
+                    int max_initial_timestamp_index, float* out_logprob, int* out_token) {
+    State& s = S();
+    const int nb = s.bs, k = nb + 1;
+    if (!ensure_lane(0, nb)) return;
+    BatchCtx& c = g_lane[0];
+    cudaStream_t st = s.stream;
+    const DecodeSpec spec = decode_spec();
+    std::vector<int> rows((size_t)nb * DEC_TOK_LD, spec.eot);
+    for (int b = 0; b < nb; ++b) memcpy(&rows[(size_t)b * DEC_TOK_LD], tokens_hist + (size_t)b * n_hist, (size_t)n_hist * sizeof(int));
+    B200_CHECK(cudaMemcpyAsync(c.tokens, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    DecodeState h{};
+    h.L = n_hist; h.pos = text_offset; h.sample_begin = sample_begin; h.sample_len = 1 << 30; h.beam_mode = 1;
+    h.without_timestamps = without_timestamps; h.max_initial_ts = max_initial_timestamp_index; h.suppress_blank = 1;
+    B200_CHECK(cudaMemcpyAsync(c.st, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    if (!g_abi_ll) {
+        bool ok = dev_alloc(&g_abi_ll, db_ll_words(s.d, s.H), true) && dev_alloc(&g_abi_barrier, (size_t)4, true);
+        if (!ok) return;
+        const unsigned one = 1;
+        B200_CHECK(cudaMemcpy(g_abi_barrier + 2, &one, sizeof(one), cudaMemcpyHostToDevice));
+    }
+    DbArgs a{};
+    a.W = 1; a.nbw = nb; a.slot_stride = nb; a.win[0] = s.cur_window;
+    a.ckv_frag = s.ckv_frag; a.ckv_window_elems = (long)s.ckv_frag_window_elems();
+    if (!fill_geometry(a, nb)) return;
+    db_carve_ll(a, g_abi_ll, s.d, s.H);
+    a.logits = s.slogits; a.ld_logits = s.V; a.mkv = s.mkv; a.kv_stride = (long)s.bs * N_TEXT_CTX * s.d; a.table = s.table; a.tokens = c.tokens;
+    a.text_offset = text_offset; a.barrier = g_abi_barrier; a.dbg_stage = -1;
+    db_launch(a, grid_ctas(), st);
+    SampleArgs sa{};
+    sa.logits = s.slogits; sa.ld_logits = s.V; sa.tokens = c.tokens; sa.st = c.st; sa.spec = spec; sa.nb = nb; sa.k = k;
+    sa.cand_lp = c.cand_lp; sa.cand_tok = c.cand_tok; sa.part = c.part;
+    sample_partial(sa, st);
+    BeamUpdateArgs ba{};
+    ba.part = c.part; ba.timestamp_begin = spec.timestamp_begin; ba.update = 0;                     // candidates only
+    ba.cand_lp = c.cand_lp; ba.cand_tok = c.cand_tok; ba.nb = nb; ba.k = k; ba.tokens = c.tokens; ba.table = s.table;
+    ba.fin_tokens = c.fin_tokens; ba.st = c.st; ba.eot = spec.eot; ba.n_text_ctx = N_TEXT_CTX;
+    beam_update(ba, st);
+    B200_CHECK(cudaMemcpyAsync(out_logprob, c.cand_lp, (size_t)nb * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaMemcpyAsync(out_token, c.cand_tok, (size_t)nb * k * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaStreamSynchronize(st));
 }
 
 __global__ void batch_init_tokens_kernel(int* tokens, const int* initial, int n, int W, int nb, int eot, int* table) {
@@ -399,7 +432,6 @@ int decode_windows_batch(const int* windows, int n_windows, const int* initial_t
 // stage timeline of the batched kernel (tools/step_timeline.py): enable allocates + clears the buffer, disable copies it out
 int batch_timeline(int enable, unsigned long long* out, int cap_ctas) {
     State& s = S();
-    mega_available();
     const size_t n = (size_t)s.n_sms * DB_DBG_LD;
     if (enable) {
         if (!g_dbg && !dev_alloc(&g_dbg, n)) return 0;

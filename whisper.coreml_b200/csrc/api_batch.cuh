@@ -15,6 +15,9 @@ int decode_windows_batch(const int* windows, int n_windows, const int* initial_t
                          int without_timestamps, int max_initial_timestamp_index, int* out_tokens, int* out_lengths,
                          float* out_sum_logprobs, float* out_no_speech, int* out_steps);
 int batch_timeline(int enable, unsigned long long* out, int cap_ctas);
+// decoder1StepFused: one token step of the process-global cache from token histories + logit filters + top-(bs + 1) per beam
+void step_fused_abi(const int* tokens_hist, int n_hist, int sample_begin, int text_offset, int without_timestamps,
+                    int max_initial_timestamp_index, float* out_logprob, int* out_token);
 DecodeSpec decode_spec();                     // api_decode.cu: the spec set by b200SetDecodeSpec
 
 }  // namespace b200

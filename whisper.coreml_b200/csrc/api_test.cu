@@ -1,11 +1,9 @@
 // Test hooks exported through the C ABI (tests/ only; see include/whisper_b200.h).
 #include <algorithm>
 #include "api_batch.cuh"
-#include "decoder_mega.cuh"
 #include "gemm.cuh"
 #include "ops.cuh"
 #include "whisper_b200.h"
-#include "decoder_step.cuh"
 
 using namespace b200;
 
@@ -199,23 +197,9 @@ extern "C" int b200TestAttentionTimeline(const void* dQKV, void* dO, int n_tok, 
 }
 
 // Stage timeline of the persistent step kernel: enable = 1 allocates/clears the buffer (every following step overwrites
-// it: mark k of CTA c = %globaltimer ns at out[c * MEGA_DBG_LD + k]; mark 0 = start, 2i+1 / 2i+2 = after the prologue /
+// it: mark k of CTA c = %globaltimer ns at out[c * DB_DBG_LD + k]; mark 0 = start, 2i+1 / 2i+2 = after the prologue /
 // body of stage i); enable = 0 copies the last step's marks of up to `cap_ctas` CTAs to `out` and returns the CTA count.
 extern "C" int b200TestStepTimeline(int enable, unsigned long long* out, int cap_ctas) {
-    State& s = S();
     use_device();
-    if (batch_available()) return batch_timeline(enable, out, cap_ctas);
-    mega_available();
-    const size_t n = (size_t)s.n_sms * MEGA_DBG_LD;
-    if (enable) {
-        if (!s.mega_dbg && !dev_alloc(&s.mega_dbg, n)) return 0;
-        B200_CHECK(cudaMemset(s.mega_dbg, 0, n * sizeof(unsigned long long)));
-        return 1;
-    }
-    if (!s.mega_dbg) return 0;
-    B200_CHECK(cudaDeviceSynchronize());
-    const int n_ctas = std::min(cap_ctas, s.n_sms);
-    B200_CHECK(cudaMemcpy(out, s.mega_dbg, (size_t)n_ctas * MEGA_DBG_LD * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    dev_free(&s.mega_dbg);
-    return n_ctas;
+    return batch_available() ? batch_timeline(enable, out, cap_ctas) : 0;
 }

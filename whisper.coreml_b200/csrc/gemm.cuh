@@ -39,7 +39,7 @@ struct GemmParams {
     long c_split_stride;
     // optional second bf16 output for the crossKV projection: per 64-column group (layer, k|v, head) a fragment-major
     // copy for the decoder step kernel - K as [keys/16][2][1 KB] tiles, V transposed as [4][c2_keys/32][1 KB] tiles
-    // (decoder_mega.cu).  Group g is a V group when (g / c2_heads) is odd.  Rows are keys (row index within the batch).
+    // (decoder_batch.cu).  Group g is a V group when (g / c2_heads) is odd.  Rows are keys (row index within the batch).
     bf16* C2;
     long c2_batch_stride;
     int c2_heads;

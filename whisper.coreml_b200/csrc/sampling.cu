@@ -27,30 +27,6 @@ void beam_update(const BeamUpdateArgs& a, cudaStream_t s) {
     B200_LAUNCH_CHECK();
 }
 
-// phase 1 in every CTA; the last CTA to publish its partial (release fence + counter) merges them and updates the beams
-__global__ void __launch_bounds__(256) sample_update_kernel(const SampleArgs a, const BeamUpdateArgs u) {
-    __shared__ int stage[DEC_MAX_BEAMS * DEC_TOK_LD];
-    __shared__ int s_last;
-    sample_partial_body<256>(a, blockIdx.x, blockIdx.y, threadIdx.x, BlockSync());
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned n = gridDim.x * gridDim.y;
-        s_last = atomicAdd(&a.part->arrivals, 1u) == n - 1;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) a.part->arrivals = 0;
-    beam_update_body<256, false>(u, stage, nullptr, threadIdx.x, BlockSync());
-}
-
-void sample_and_update(const SampleArgs& a, const BeamUpdateArgs& u, cudaStream_t s) {
-    dim3 grid(SAMPLE_CHUNKS, a.nb);
-    sample_update_kernel<<<grid, 256, 0, s>>>(a, u);
-    B200_LAUNCH_CHECK();
-}
-
 // batched windows: blockIdx.z = window; the last CTA of a window to publish its partial updates that window's beams
 __global__ void __launch_bounds__(256) sample_update_batch_kernel(const SampleBatchArgs b) {
     __shared__ int stage[DEC_MAX_BEAMS * DEC_TOK_LD];

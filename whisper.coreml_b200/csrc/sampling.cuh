@@ -61,8 +61,6 @@ struct BeamUpdateArgs {
     int eot, n_text_ctx;
 };
 void beam_update(const BeamUpdateArgs& a, cudaStream_t s);
-// Both phases in ONE launch: the CTA whose partial arrives last runs phase 2 (one kernel boundary less per token step).
-void sample_and_update(const SampleArgs& a, const BeamUpdateArgs& u, cudaStream_t s);
 
 // ---- batched windows: one launch samples and updates every window of a batched decoder step --------------------------------
 // Window w owns rows [w * slot_stride, w * slot_stride + nb) of tokens / table, st[w], part[w], fin_tokens[w], cand_*[w]; the

@@ -1,5 +1,5 @@
 // Device bodies of the sampling kernels, shared by the stand-alone kernels (sampling.cu) and the persistent
-// decoder step kernel (decoder_mega.cu).
+// decoder step kernel (decoder_batch.cu).
 #pragma once
 #include "sampling.cuh"
 

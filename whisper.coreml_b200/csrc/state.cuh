@@ -10,6 +10,7 @@
 namespace b200 {
 
 constexpr int N_AUDIO_CTX = 1500, N_FRAMES = 3000, N_TEXT_CTX = 448, PREFILL_CTX = 256;
+constexpr int STEP_MAX_BEAMS = 8;         // KV-cache slots / beams of one decode (loadDecoder256's beam_size)
 constexpr int CROSS_KEYS_PAD = 1504;      // 1500 audio keys padded to a multiple of 32 for the fragment-major copy
 
 struct EncLayer {
@@ -22,7 +23,6 @@ struct DecLayer {
     DecLinear qkv, attn_out, cross_q, cross_out, mlp1, mlp2;
 };
 
-constexpr int MAX_LANES = 8;              // window decodes that may run concurrently, each on its share of the SMs
 
 struct State {
     int device = 0;
@@ -66,19 +66,9 @@ struct State {
     // prefill workspace (256 rows)
     float *px = nullptr, *pmask = nullptr, *pchw = nullptr, *pout = nullptr;
     bf16 *py = nullptr, *pqkv = nullptr, *patt = nullptr, *phid = nullptr, *pq = nullptr;
-    // step workspace (<= 8 beams)
-    float *sx = nullptr, *sqkv = nullptr, *sq = nullptr, *slogits = nullptr, *smask = nullptr, *spart = nullptr;
-    bf16 *satt = nullptr, *shid = nullptr;
-    int* scounters = nullptr;
-    // persistent step kernel (decoder_mega.cu)
-    void* mega_model = nullptr;       // MegaModel on the device
-    float* sxin = nullptr;
-    uint2* mega_ll = nullptr;         // LL activation words (decoder_mega.cuh: MegaArgs::ll_*)
-    unsigned* mega_barrier = nullptr; // [0] arrivals, [1] leavers, [2] launch sequence number
+    // reference-ABI step (decoder1Predict): logits out, mask / embedded tokens in
+    float *slogits = nullptr, *smask = nullptr, *sxin = nullptr;
     int smem_optin = 0;
-    unsigned long long* mega_dbg = nullptr;   // stage timeline buffer (b200TestStepTimeline)
-    int mega_ctas = 0;                // CTAs of the next persistent step launch (0 = all SMs)
-    int step_impl = -1;               // -1 undecided, 0 persistent kernel, 1 one kernel per stage (B200_STEP_IMPL=v1)
     int n_sms = 0;
     float* pin_logits = nullptr;      // pinned host staging
     float* pin_x = nullptr;
@@ -122,9 +112,4 @@ bool ensure_encoder_capacity(int n_windows);
 void run_encoder(const float* d_mel, long total_frames, long valid_frames, int n_windows);   // seeks already in S().d_seeks
 void run_cross_kv(int n_windows);
 void run_prefill(int beam_idx, bool want_chw, int rows);                            // px/pmask -> pout (+ pchw), KV rows -> slot
-// sx -> slogits; d_t / d_skip: optional device-side text_offset and no-op flag (device-driven decode loop)
-void run_step(int nb, int text_offset, const float* d_mask, bool want_logits, const int* d_t, const int* d_skip);
-bool mega_available();
-void decode_free_lanes();            // api_decode.cu: releases the extra decode lanes               // persistent step kernel usable for the loaded model?
-
 }  // namespace b200
