@@ -136,15 +136,27 @@ void b200SelectWindow(int w);
 int b200DecodeWindow(const int* initial_tokens, int n_initial, int beam_size, int sample_len,
                      int without_timestamps, int max_initial_timestamp_index,
                      int* out_tokens, int* out_lengths, float* out_sum_logprobs, float* out_no_speech);
-/* The same for n_windows encoded windows (ids as for b200SelectWindow).  Independent windows are decoded CONCURRENTLY:
- * up to 2 decode lanes, each with its own KV cache, decode state and stream, each step kernel on its share of the SMs
- * (the token loop is latency bound, so two lanes nearly double the throughput; B200_DECODE_LANES=1 disables it).
+/* The same for n_windows encoded windows (ids as for b200SelectWindow).  Independent windows are decoded CONCURRENTLY on up to
+ * 8 decode lanes (B200_DECODE_LANES), each lane with its own KV cache, decode states and stream and its share of the SMs; the
+ * windows of a lane (more than one from nine windows up, or with fewer lanes) advance together in ONE batched step kernel, so a
+ * lane streams the decoder weights once per step for all of them.  The token loop is a latency-bound chain of dependent stages:
+ * lanes overlap each other's stalls, batching saves weight traffic.
  * Outputs are the b200DecodeWindow outputs per window, window-major: out_tokens (n_windows, n_cand, 449), out_lengths and
  * out_sum_logprobs (n_windows, n_cand), out_no_speech (n_windows), out_steps (n_windows, may be NULL).
  * Returns the total number of sampling steps.  This is what transcribe() calls (whisper/transcribe.py:276-306 loops windows). */
 int b200DecodeWindows(const int* windows, int n_windows, const int* initial_tokens, int n_initial, int beam_size,
                       int sample_len, int without_timestamps, int max_initial_timestamp_index, int* out_tokens,
                       int* out_lengths, float* out_sum_logprobs, float* out_no_speech, int* out_steps);
+/* The same with sampling at temperature > 0 (the reference's fallback decodes, whisper/transcribe.py:188-228): beam_size <= 0,
+ * n_group = best_of independent samples per window (GreedyDecoder over n_group rows, whisper/decoding.py:299-325, 761), every
+ * token drawn from Categorical(logits / temperature) after the logit filters (:307-310) with a counter-based generator
+ * (Philox4x32-10 keyed by `seed`; window, row, step and token index form the counter, so a decode is reproducible and
+ * independent of batching); sum_logprobs accumulate log_softmax(logits) of the drawn tokens (:311-313).  n_cand = n_group.
+ * temperature == 0 is b200DecodeWindows. */
+int b200DecodeWindowsEx(const int* windows, int n_windows, const int* initial_tokens, int n_initial, int beam_size, int n_group,
+                        float temperature, unsigned long long seed, int sample_len, int without_timestamps,
+                        int max_initial_timestamp_index, int* out_tokens, int* out_lengths, float* out_sum_logprobs,
+                        float* out_no_speech, int* out_steps);
 
 /* decoder1 with on-device filters + log-softmax + top-(bs+1) instead of returning full logits:
  * tokens_hist (bs, n_hist) int32 HOST = whole context so far (last column is fed to the

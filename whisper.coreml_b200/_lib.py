@@ -46,6 +46,7 @@ SIGNATURES = {
     "crossKVPredictWindows": (None, [c_int]),
     "b200DecodeWindow": (c_int, [i32p, c_int, c_int, c_int, c_int, c_int, i32p, i32p, f32p, f32p]),
     "b200DecodeWindows": (c_int, [i32p, c_int, i32p, c_int, c_int, c_int, c_int, c_int, i32p, i32p, f32p, f32p, i32p]),
+    "b200DecodeWindowsEx": (c_int, [i32p, c_int, i32p, c_int, c_int, c_int, c_float, ctypes.c_ulonglong, c_int, c_int, c_int, i32p, i32p, f32p, f32p, i32p]),
     "decoder1StepFused": (None, [i32p, c_int, c_int, c_int, c_int, c_int, f32p, i32p]),
     "medianFilter": (None, [f32p, f32p, c_long, c_int, c_int]),
     "dtw": (c_int, [f32p, c_int, c_int, i32p, i32p]),

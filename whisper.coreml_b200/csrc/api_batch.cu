@@ -270,8 +270,8 @@ static int emit_window(const DecodeState& h, const int* tok, const int* fin, int
         while (n_initial + l < len && seq[n_initial + l] != eot) ++l;  // tokens before the first EOT after sample_begin (:776-779)
         out_lengths[n_cand] = l; out_sum_logprobs[n_cand] = score; ++n_cand;
     };
-    if (!h.beam_mode) {
-        emit(tok, h.L, h.sum_lp[0]);
+    if (!h.beam_mode) {                                                 // GreedyDecoder.finalize (:320-325): every row is a candidate
+        for (int b = 0; b < nb; ++b) emit(tok + (size_t)b * DEC_TOK_LD, h.L, h.sum_lp[b]);
     } else {
         for (int f = 0; f < h.n_finished; ++f) emit(fin + (size_t)f * DEC_TOK_LD, h.fin_len[f], h.fin_score[f]);
         if (n_cand < nb) {                                              // not enough finished: add live beams, best first (:418-424)
@@ -307,12 +307,13 @@ static void lane_issue(BatchJob& j) {
 // Windows are spread over up to B200_DECODE_LANES (default 8) concurrent lanes; a lane takes ceil(n / lanes) windows per batched
 // step (B200_BATCH_WINDOWS caps it).  Up to 8 windows that is one window per lane - measured faster than one wide batch while
 // the step is latency bound - beyond that the lanes' batches grow.
-int decode_windows_batch(const int* windows, int n_windows, const int* initial_tokens, int n_initial, int beam_size, int sample_len,
+int decode_windows_batch(const int* windows, int n_windows, const int* initial_tokens, int n_initial, int beam_size, int n_group,
+                         float temperature, unsigned long long seed, int sample_len,
                          int without_timestamps, int max_initial_timestamp_index, int* out_tokens, int* out_lengths,
                          float* out_sum_logprobs, float* out_no_speech, int* out_steps) {
     State& s = S();
     const DecodeSpec spec = decode_spec();
-    const int nb = beam_size > 0 ? beam_size : 1, cand = nb;
+    const int nb = beam_size > 0 ? beam_size : (n_group > 0 ? n_group : 1), cand = nb;
     static const int max_lanes = [] { const char* e = getenv("B200_DECODE_LANES"); const int v = e ? atoi(e) : MAX_DECODE_LANES; return v < 1 ? 1 : (v > MAX_DECODE_LANES ? MAX_DECODE_LANES : v); }();
     const int w_max = batch_max_windows(nb);
     int sot_index = -1;
@@ -348,7 +349,8 @@ int decode_windows_batch(const int* windows, int n_windows, const int* initial_t
         h.L = n_initial; h.pos = n_initial - 1; h.sample_begin = n_initial; h.sample_len = sample_len;
         h.beam_mode = beam_size > 0; h.without_timestamps = without_timestamps; h.max_initial_ts = max_initial_timestamp_index;
         h.suppress_blank = 1; h.no_speech_prob = NAN;
-        const std::vector<DecodeState> hs0(DB_MAX_WINDOWS, h);
+        h.temperature = beam_size > 0 ? 0.f : temperature; h.seed_lo = (unsigned)seed; h.seed_hi = (unsigned)(seed >> 32);
+        std::vector<DecodeState> hs0(DB_MAX_WINDOWS, h);
         {
             // all beams hold the same tokens (decoding.py:761), so the prompt runs as n_initial one-row-per-window steps into the
             // window's first cache slot: a causal prefill over n rows IS n steps, and the step kernel streams each weight once
@@ -358,7 +360,9 @@ int decode_windows_batch(const int* windows, int n_windows, const int* initial_t
             for (int i = 0; i < n_jobs; ++i) {
                 BatchJob& j = job[i];
                 BatchCtx& c = g_lane[j.lane];
+                for (int q = 0; q < j.W; ++q) hs0[q].stream = (unsigned)j.windows[q];       // every window draws from its own random stream
                 B200_CHECK(cudaMemcpyAsync(c.st, hs0.data(), (size_t)j.W * sizeof(DecodeState), cudaMemcpyHostToDevice, c.stream));
+                B200_CHECK(cudaStreamSynchronize(c.stream));                            // (hs0 is rewritten for the next lane)
                 B200_CHECK(cudaMemcpyAsync(c.d_init, initial_tokens, (size_t)n_initial * sizeof(int), cudaMemcpyHostToDevice, c.stream));
                 batch_init_tokens_kernel<<<1, 1024, 0, c.stream>>>(c.tokens, c.d_init, n_initial, j.W, nb, spec.eot, c.table);
                 B200_LAUNCH_CHECK();

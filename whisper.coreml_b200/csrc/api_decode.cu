@@ -127,14 +127,17 @@ void crossKVPredictWindows(int n_windows) {
 
 extern "C" {
 
-int b200DecodeWindows(const int* windows, int n_windows, const int* initial_tokens, int n_initial, int beam_size, int sample_len,
-                      int without_timestamps, int max_initial_timestamp_index, int* out_tokens, int* out_lengths,
-                      float* out_sum_logprobs, float* out_no_speech, int* out_steps) {
+int b200DecodeWindowsEx(const int* windows, int n_windows, const int* initial_tokens, int n_initial, int beam_size, int n_group,
+                        float temperature, unsigned long long seed, int sample_len, int without_timestamps,
+                        int max_initial_timestamp_index, int* out_tokens, int* out_lengths, float* out_sum_logprobs,
+                        float* out_no_speech, int* out_steps) {
     State& s = S();
     DecodeCtx& c = g_dc;
     if (!s.dec1_loaded || !s.dec256_loaded || !s.ckv_loaded) { record_error("b200DecodeWindows: decoder256 / decoder1 / crossKV not loaded"); return 0; }
-    const int nb = beam_size > 0 ? beam_size : 1;
-    if (nb > STEP_MAX_BEAMS) { record_error("b200DecodeWindows: %d beams (at most %d)", nb, STEP_MAX_BEAMS); return 0; }
+    const int nb = beam_size > 0 ? beam_size : (n_group > 0 ? n_group : 1);
+    if (nb > STEP_MAX_BEAMS) { record_error("b200DecodeWindows: %d beams / samples (at most %d)", nb, STEP_MAX_BEAMS); return 0; }
+    if (beam_size > 0 && temperature != 0.f) { record_error("b200DecodeWindows: beam search runs at temperature 0 (whisper/transcribe.py:196-202)"); return 0; }
+    if (temperature < 0.f) { record_error("b200DecodeWindows: temperature %g", temperature); return 0; }
     if (n_initial < 1 || n_initial > PREFILL_CTX) { record_error("b200DecodeWindows: n_initial %d outside [1, 256]", n_initial); return 0; }
     if (n_windows < 1 || sample_len < 1) return 0;
     for (int w = 0; w < n_windows; ++w)
@@ -143,8 +146,15 @@ int b200DecodeWindows(const int* windows, int n_windows, const int* initial_toke
     if (c.spec.n_vocab != s.V || c.spec.eot < 0) { record_error("decode: call b200SetDecodeSpec (n_vocab %d) first", s.V); return 0; }
     if (!batch_available()) { record_error("b200DecodeWindows: the step kernel does not support these dimensions (n_state %d, %d layers)", s.d, s.Ld); return 0; }
     // windows are spread over concurrent decode lanes, every lane advancing its windows in ONE batched step kernel (api_batch.cu)
-    return decode_windows_batch(windows, n_windows, initial_tokens, n_initial, beam_size, sample_len, without_timestamps,
-                                max_initial_timestamp_index, out_tokens, out_lengths, out_sum_logprobs, out_no_speech, out_steps);
+    return decode_windows_batch(windows, n_windows, initial_tokens, n_initial, beam_size, n_group, temperature, seed, sample_len,
+                                without_timestamps, max_initial_timestamp_index, out_tokens, out_lengths, out_sum_logprobs, out_no_speech, out_steps);
+}
+
+int b200DecodeWindows(const int* windows, int n_windows, const int* initial_tokens, int n_initial, int beam_size, int sample_len,
+                      int without_timestamps, int max_initial_timestamp_index, int* out_tokens, int* out_lengths,
+                      float* out_sum_logprobs, float* out_no_speech, int* out_steps) {
+    return b200DecodeWindowsEx(windows, n_windows, initial_tokens, n_initial, beam_size, 1, 0.f, 0ull, sample_len, without_timestamps,
+                               max_initial_timestamp_index, out_tokens, out_lengths, out_sum_logprobs, out_no_speech, out_steps);
 }
 
 int b200DecodeWindow(const int* initial_tokens, int n_initial, int beam_size, int sample_len, int without_timestamps,

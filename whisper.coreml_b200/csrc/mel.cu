@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "state.cuh"
 #include "whisper_b200.h"
 
 namespace b200 {
@@ -177,6 +178,7 @@ static bool init_tables(int n_mels) {
     if (!ok) { record_error("log-mel: table allocation failed"); t.twiddle = nullptr; return false; }
     mel_tables_kernel<<<cdiv(199 * BIN_LD, 256), 256>>>(t.twiddle, t.window);
     B200_LAUNCH_CHECK();
+    B200_CHECK(cudaDeviceSynchronize());                                // one-time: the frames kernels run on the library stream
     return true;
 }
 
@@ -205,25 +207,39 @@ long log_mel_device(const float* d_audio, long n_samples, long padding, int n_me
 
 using namespace b200;
 
+// d_audio may have been produced on the caller's stream (torch's default stream): wait for it once, then run on the library
+// stream under the mel stage timer; the result is complete when the call returns.
 extern "C" long logMelSpectrogramDev(const float* d_audio, long n_samples, long padding, int n_mels, float* d_out_mel) {
-    const long f = log_mel_device(d_audio, n_samples, padding, n_mels, d_out_mel, 0);
-    B200_CHECK(cudaStreamSynchronize(0));
+    use_device();
+    B200_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
+    cudaStream_t st = S().stream;
+    long f;
+    {
+        StageTimer t(ST_MEL);
+        f = log_mel_device(d_audio, n_samples, padding, n_mels, d_out_mel, st);
+    }
+    B200_CHECK(cudaStreamSynchronize(st));
     return f;
 }
 
+// host buffers in and out: staged through two grow-only device buffers (no allocation per call)
 extern "C" long logMelSpectrogram(const float* audio, long n_samples, long padding, int n_mels, float* out_mel) {
-    float *d_a = nullptr, *d_o = nullptr;
+    static float *d_a = nullptr, *d_o = nullptr;
+    static size_t cap_a = 0, cap_o = 0;
+    use_device();
+    cudaStream_t st = S().stream;
     const long n_frames = (n_samples + padding) / HOP;
-    if (cudaMalloc((void**)&d_a, (size_t)(n_samples > 0 ? n_samples : 1) * sizeof(float)) != cudaSuccess ||
-        cudaMalloc((void**)&d_o, (size_t)(n_frames > 0 ? n_frames : 1) * n_mels * sizeof(float)) != cudaSuccess) {
-        record_error("logMelSpectrogram: device allocation failed");
-        if (d_a) cudaFree(d_a);
-        return 0;
+    const size_t need_a = (size_t)(n_samples > 0 ? n_samples : 1), need_o = (size_t)(n_frames > 0 ? n_frames : 1) * n_mels;
+    if (need_a > cap_a) { if (d_a) cudaFree(d_a); d_a = nullptr; cap_a = 0; if (cudaMalloc((void**)&d_a, need_a * sizeof(float)) == cudaSuccess) cap_a = need_a; }
+    if (need_o > cap_o) { if (d_o) cudaFree(d_o); d_o = nullptr; cap_o = 0; if (cudaMalloc((void**)&d_o, need_o * sizeof(float)) == cudaSuccess) cap_o = need_o; }
+    if (cap_a < need_a || cap_o < need_o) { record_error("logMelSpectrogram: device allocation failed"); return 0; }
+    B200_CHECK(cudaMemcpyAsync(d_a, audio, (size_t)n_samples * sizeof(float), cudaMemcpyHostToDevice, st));
+    long f;
+    {
+        StageTimer t(ST_MEL);
+        f = log_mel_device(d_a, n_samples, padding, n_mels, d_o, st);
     }
-    B200_CHECK(cudaMemcpyAsync(d_a, audio, (size_t)n_samples * sizeof(float), cudaMemcpyHostToDevice, 0));
-    const long f = log_mel_device(d_a, n_samples, padding, n_mels, d_o, 0);
-    B200_CHECK(cudaMemcpyAsync(out_mel, d_o, (size_t)f * n_mels * sizeof(float), cudaMemcpyDeviceToHost, 0));
-    B200_CHECK(cudaStreamSynchronize(0));
-    cudaFree(d_a); cudaFree(d_o);
+    B200_CHECK(cudaMemcpyAsync(out_mel, d_o, (size_t)f * n_mels * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaStreamSynchronize(st));
     return f;
 }

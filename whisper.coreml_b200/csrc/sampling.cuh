@@ -23,6 +23,8 @@ struct DecodeState {                   // one per decode, in device memory
     int n_finished;
     int sample_begin, sample_len, beam_mode, without_timestamps, max_initial_ts, suppress_blank;
     float no_speech_prob;
+    float temperature;                 // 0: argmax / beam search; > 0: Categorical(logits / temperature) per row (decoding.py:307-310)
+    unsigned seed_lo, seed_hi, stream;  // counter-based RNG key and the decode's stream id (window), see sampling_dev.cuh
     float sum_lp[DEC_MAX_BEAMS];
     float fin_score[DEC_MAX_BEAMS];
     int fin_len[DEC_MAX_BEAMS];
@@ -35,6 +37,7 @@ constexpr int SAMPLE_CHUNK_TOKENS_MAX = 2048;   // tokens one (chunk, beam) CTA 
 struct SamplePartials {                // device scratch
     float m[DEC_MAX_BEAMS][SAMPLE_CHUNKS], s[DEC_MAX_BEAMS][SAMPLE_CHUNKS];
     float topv[DEC_MAX_BEAMS][SAMPLE_CHUNKS][SAMPLE_MAX_K];
+    float topx[DEC_MAX_BEAMS][SAMPLE_CHUNKS];      // temperature > 0: the UNPERTURBED logit of the chunk's winner (topv holds logit / T + Gumbel noise)
     int topi[DEC_MAX_BEAMS][SAMPLE_CHUNKS][SAMPLE_MAX_K];
     unsigned arrivals;                 // CTAs of the fused kernel that have written their partial (re-armed by the last one)
 };

@@ -51,6 +51,25 @@ __device__ __forceinline__ void probe(int idx, int tid) { if (g_probe && tid == 
 __device__ __forceinline__ void probe(int, int) {}
 #endif
 
+// ---- Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"): a counter-based generator, so every
+// (decode stream, row, step, token) draws its own number with no state to carry between kernels ----------------------------
+__device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+// Gumbel(0, 1) noise for token v: argmax_v (logit_v / T + G_v) is a draw from Categorical(logits / T)
+__device__ __forceinline__ float gumbel_noise(const DecodeState& st, int row, int v) {
+    const uint32_t r = philox_first((uint32_t)v, (uint32_t)st.step, (uint32_t)row, st.stream, st.seed_lo, st.seed_hi);
+    const float u = ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f);      // (0, 1), 24 bits
+    return -__logf(-__logf(u));
+}
+
 constexpr int SP_CHUNK_MAX = SAMPLE_CHUNK_TOKENS_MAX;                     // >= largest chunk (1799 text / 1502 timestamp tokens)
 
 // One (chunk, beam) unit; `tid` in [0, SP_THREADS); sync() is a barrier over exactly those SP_THREADS threads (256 in the
@@ -140,9 +159,22 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
         for (int w = 1; w < SP_WARPS; ++w) online_merge(m, s, red_m[w], red_s[w]);
         a.part->m[b][chunk] = m; a.part->s[b][chunk] = s;
     }
+    // temperature > 0 (greedy rows only): the selection key becomes logit / T + Gumbel noise; the log-softmax partial above stays
+    // that of the unperturbed logits (decoding.py:307-313), and the winner's plain logit travels along (topx)
+    const float temp = st.temperature;
+    float plain[SP_PER_THREAD];
+    if (temp > 0.f) {
+        const float inv_t = 1.f / temp;
+#pragma unroll
+        for (int e = 0; e < SP_PER_THREAD; ++e) {
+            plain[e] = val[e];
+            const int v = lo + e * SP_THREADS + tid;
+            if (v < hi && val[e] != -INFINITY) val[e] = fmaf(val[e], inv_t, gumbel_noise(st, b, v));
+        }
+    }
     // chunk-local top-k (ties -> lowest index) in two levels: every warp extracts its own top-k from the register-resident
     // values with shuffles only, then warp 0 merges the <= 8 * k survivors - one block barrier instead of two per rank
-    __shared__ float wv[8][SAMPLE_MAX_K]; __shared__ int wi[8][SAMPLE_MAX_K];
+    __shared__ float wv[8][SAMPLE_MAX_K]; __shared__ int wi[8][SAMPLE_MAX_K]; __shared__ float wx[8];
     probe(303, tid);
     unsigned taken = 0;
     for (int c = 0; c < a.k; ++c) {
@@ -158,7 +190,15 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
         if (lane == 0) { wv[warp][c] = bv; wi[warp][c] = bi; }
-        if (bi != 0x7fffffff && (bi - lo) % SP_THREADS == tid) taken |= 1u << ((bi - lo) / SP_THREADS);   // a picked slot never competes again
+        if (bi != 0x7fffffff && (bi - lo) % SP_THREADS == tid) {
+            taken |= 1u << ((bi - lo) / SP_THREADS);         // a picked slot never competes again
+            if (temp > 0.f && c == 0) {                       // the owner of the warp's winner publishes its plain logit
+                float px = -INFINITY;
+#pragma unroll
+                for (int e = 0; e < SP_PER_THREAD; ++e) if (e == (bi - lo) / SP_THREADS) px = plain[e];
+                wx[warp] = px;
+            }
+        }
     }
     sync();
     probe(304, tid);
@@ -185,7 +225,11 @@ __device__ __forceinline__ void sample_partial_body(const SampleArgs& a, int chu
             if (lane == 0) { a.part->topv[b][chunk][c] = bv; a.part->topi[b][chunk][c] = bi; }
             if (bi != 0x7fffffff) {
 #pragma unroll
-                for (int e = 0; e < 3; ++e) if (ci[e] == bi) tk |= 1u << e;       // token indices are unique
+                for (int e = 0; e < 3; ++e)
+                    if (ci[e] == bi) {
+                        tk |= 1u << e;                            // token indices are unique
+                        if (temp > 0.f && c == 0) a.part->topx[b][chunk] = wx[(lane + 32 * e) / a.k];      // the winner's warp
+                    }
             }
         }
     }
@@ -238,6 +282,7 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
             cv[e] = -INFINITY; ci[e] = 0x7fffffff;
             if (mine && e < a.k) { cv[e] = __ldcg(&P.topv[warp][lane][e]); ci[e] = __ldcg(&P.topi[warp][lane][e]); }
         }
+        const float px = (st.temperature > 0.f && mine) ? __ldcg(&P.topx[warp][lane]) : -INFINITY;   // plain logit of the chunk's winner
         unsigned taken = 0;
         for (int c = 0; c < a.k; ++c) {
             float bv = -INFINITY; int bi = 0x7fffffff;
@@ -248,6 +293,10 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
             for (int o = 16; o > 0; o >>= 1) {
                 const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (st.temperature > 0.f) {                      // sampled token: its log-probability comes from the unperturbed logit
+                const unsigned who = __ballot_sync(0xffffffffu, bi != 0x7fffffff && ci[0] == bi);
+                bv = who ? __shfl_sync(0xffffffffu, px, __ffs(who) - 1) : -INFINITY;
             }
             if (bi != 0x7fffffff) {
 #pragma unroll
@@ -283,12 +332,15 @@ __device__ __forceinline__ void beam_update_body(const BeamUpdateArgs& a, int* s
     }
     if (tid == 0) {
         int nfin_new = 0, done = 0;
-        if (!st.beam_mode) {
-            const int tok = c_tok[0], last = tok_src[L - 1];
-            nsrc[0] = 0;
-            ntok[0] = last == a.eot ? a.eot : tok;
-            nsum[0] = st.sum_lp[0] + (last == a.eot ? 0.f : c_lp[0]);
-            done = ntok[0] == a.eot;
+        if (!st.beam_mode) {                             // GreedyDecoder.update (:303-318): every row (best_of samples at T > 0) on its own
+            done = 1;
+            for (int b = 0; b < nb; ++b) {
+                const int tok = c_tok[b * a.k], last = tok_src[b * DEC_TOK_LD + L - 1];
+                nsrc[b] = b;
+                ntok[b] = last == a.eot ? a.eot : tok;
+                nsum[b] = st.sum_lp[b] + (last == a.eot ? 0.f : c_lp[b * a.k]);
+                done = done && ntok[b] == a.eot;
+            }
         } else {
             const int nsb = st.step == 0 ? 1 : nb;      // identical prefixes at step 0 collapse to one key set (:366-373)
             const int n = nsb * a.k;                     // sc / id were ranked by all threads above (stable, descending, :377)

@@ -1,7 +1,7 @@
-"""Decoding: counterpart of whisper/decoding.py for the paths the fork runs (temperature 0; greedy or
-beam search; one audio window per call).  The loop itself - logits, logit filters, log-softmax, top-k,
-beam bookkeeping, KV-cache permutation (decoding.py:707-737, 350-409, 450-532, 189-204) - executes on
-the device inside b200DecodeWindow; this module prepares the initial tokens and ranks the candidates
+"""Decoding: counterpart of whisper/decoding.py for the paths the fork runs (greedy, beam search at temperature 0, best_of
+sampling at temperature > 0; one audio window per decode, many windows per call).  The loop itself - logits, logit filters,
+log-softmax, top-k / Categorical sampling, beam bookkeeping, KV-cache permutation (decoding.py:707-737, 299-409, 450-532,
+189-204) - executes on the device inside b200DecodeWindowsEx; this module prepares the initial tokens and ranks the candidates
 (MaximumLikelihoodRanker, decoding.py:217-240)."""
 from __future__ import annotations
 
@@ -19,12 +19,14 @@ class DecodingOptions:                       # subset of whisper/decoding.py:81-
     language: Optional[str] = "en"
     temperature: float = 0.0
     sample_len: Optional[int] = None
+    best_of: Optional[int] = None                # independent samples per window at temperature > 0 (decoding.py:88)
     beam_size: Optional[int] = None
     patience: Optional[float] = None
     length_penalty: Optional[float] = None
     prompt: Optional[Sequence[int]] = None
     without_timestamps: bool = False
     max_initial_timestamp: Optional[float] = 1.0
+    seed: int = 0                                # key of the device's counter-based sampler (temperature > 0)
 
 
 @dataclass(frozen=True)
@@ -35,13 +37,20 @@ class DecodingResult:                        # whisper/decoding.py:118-128
     sum_logprob: float = np.nan
     steps: int = 0
     candidates: int = 0
+    temperature: float = 0.0
 
 
 def decode_windows(model, options: DecodingOptions, windows: Sequence[int]) -> List[DecodingResult]:
     """DecodingTask.run (decoding.py:740-816) for several windows already encoded on the device.  The windows are
     independent (condition_on_previous_text=False), so the library decodes them concurrently (b200DecodeWindows)."""
-    if options.temperature != 0.0:
-        raise NotImplementedError("sampling at temperature > 0 (decoding.py:307-310) is not on the B200 hot path")
+    if options.temperature < 0.0:
+        raise ValueError("temperature must be >= 0")
+    if options.beam_size is not None and options.best_of is not None:
+        raise ValueError("beam_size and best_of can't be given together")            # decoding.py:543
+    if options.temperature == 0.0 and options.best_of is not None:
+        raise ValueError("best_of with greedy sampling (T=0) is not compatible")      # decoding.py:545-546
+    if options.temperature > 0.0 and options.beam_size is not None:
+        raise ValueError("beam search runs at temperature 0 (whisper/transcribe.py:196-202 drops beam_size for t > 0)")
     if options.patience not in (None, 1.0):
         raise NotImplementedError("patience != 1")
     if options.prompt:
@@ -54,7 +63,8 @@ def decode_windows(model, options: DecodingOptions, windows: Sequence[int]) -> L
     n_ctx = model.dims.n_text_ctx
     sample_len = options.sample_len or n_ctx // 2
     bs = options.beam_size or 0
-    n_cand = max(bs, 1)
+    n_group = 1 if bs else (options.best_of or 1)                           # decoding.py:549
+    n_cand = max(bs, n_group)
     max_ts = -1
     if options.max_initial_timestamp:
         max_ts = round(options.max_initial_timestamp / 0.02)              # decoding.py:591-594 (time_precision 30/1500)
@@ -64,10 +74,11 @@ def decode_windows(model, options: DecodingOptions, windows: Sequence[int]) -> L
     toks = np.empty((nw, n_cand, n_ctx + 1), dtype=np.int32)
     lens = np.empty((nw, n_cand), dtype=np.int32); lps = np.empty((nw, n_cand), dtype=np.float32)
     nsp = np.empty(nw, dtype=np.float32); steps = np.zeros(nw, dtype=np.int32)
-    model.lib.b200DecodeWindows(wins.ctypes.data_as(_lib.i32p), nw, init.ctypes.data_as(_lib.i32p), len(init), bs, sample_len,
-                                1 if options.without_timestamps else 0, max_ts,
-                                toks.ctypes.data_as(_lib.i32p), lens.ctypes.data_as(_lib.i32p),
-                                lps.ctypes.data_as(_lib.f32p), nsp.ctypes.data_as(_lib.f32p), steps.ctypes.data_as(_lib.i32p))
+    model.lib.b200DecodeWindowsEx(wins.ctypes.data_as(_lib.i32p), nw, init.ctypes.data_as(_lib.i32p), len(init), bs, n_group,
+                                  float(options.temperature), int(options.seed) & 0xFFFFFFFFFFFFFFFF, sample_len,
+                                  1 if options.without_timestamps else 0, max_ts,
+                                  toks.ctypes.data_as(_lib.i32p), lens.ctypes.data_as(_lib.i32p),
+                                  lps.ctypes.data_as(_lib.f32p), nsp.ctypes.data_as(_lib.f32p), steps.ctypes.data_as(_lib.i32p))
     _lib.check_errors("b200DecodeWindows")
     out = []
     n0 = len(initial)
@@ -83,7 +94,7 @@ def decode_windows(model, options: DecodingOptions, windows: Sequence[int]) -> L
         best = valid[int(np.argmax(scores))]
         tokens = toks[w, best, n0:n0 + lens[w, best]].tolist()
         out.append(DecodingResult(tokens=tokens, avg_logprob=float(lps[w, best]) / (len(tokens) + 1), no_speech_prob=float(nsp[w]),
-                                  sum_logprob=float(lps[w, best]), steps=int(steps[w]), candidates=len(valid)))
+                                  sum_logprob=float(lps[w, best]), steps=int(steps[w]), candidates=len(valid), temperature=float(options.temperature)))
     return out
 
 

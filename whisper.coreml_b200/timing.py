@@ -98,3 +98,87 @@ def find_alignment(model, tokenizer, text_tokens: List[int], num_frames: int, *,
     end_times = al.jump_times[word_boundaries[1:]]
     probs = [float(np.mean(al.text_token_probs[i:j])) for i, j in zip(word_boundaries[:-1], word_boundaries[1:])]
     return [WordTiming(w, t, float(s), float(e), p) for w, t, s, e, p in zip(words, word_tokens, start_times, end_times, probs)]
+
+
+PREPEND_PUNCTUATIONS = "\"'“¿([{-"
+APPEND_PUNCTUATIONS = "\"'.。,，!！?？:：”)]}、"
+SENTENCE_END_MARKS = ".。!！?？"
+
+
+def merge_punctuations(alignment: List[WordTiming], prepended: str = PREPEND_PUNCTUATIONS, appended: str = APPEND_PUNCTUATIONS) -> None:
+    """whisper/timing.py:234-265: glue leading punctuation to the word that follows it and trailing punctuation to the word before
+    it (in place; a merged-away entry keeps an empty word and no tokens)."""
+    # right to left: " (" + "word" -> " (word"; `tgt` is the nearest entry to the right that is not itself being prepended
+    tgt = len(alignment) - 1
+    for i in range(len(alignment) - 2, -1, -1):
+        cur, nxt = alignment[i], alignment[tgt]
+        if cur.word.startswith(" ") and cur.word.strip() in prepended:
+            nxt.word, nxt.tokens = cur.word + nxt.word, cur.tokens + nxt.tokens
+            cur.word, cur.tokens = "", []
+        else:
+            tgt = i
+    # left to right: "word" + "." -> "word."; `tgt` is the nearest entry to the left that still owns text
+    tgt = 0
+    for j in range(1, len(alignment)):
+        prev, cur = alignment[tgt], alignment[j]
+        if not prev.word.endswith(" ") and cur.word in appended:
+            prev.word, prev.tokens = prev.word + cur.word, prev.tokens + cur.tokens
+            cur.word, cur.tokens = "", []
+        else:
+            tgt = j
+
+
+def add_word_timestamps(segments: List[dict], alignment: List[WordTiming], eot: int, *, last_speech_timestamp: float,
+                        prepend_punctuations: str = PREPEND_PUNCTUATIONS, append_punctuations: str = APPEND_PUNCTUATIONS) -> float:
+    """whisper/timing.py:268-376 after its find_alignment call: `alignment` holds the word timings of the text tokens of all
+    `segments` of one window (times relative to the window).  Clamps over-long words next to sentence ends and after pauses,
+    merges punctuation, distributes the words over the segments and reconciles segment and word boundaries.  Adds "words" to
+    every segment and returns the updated last_speech_timestamp."""
+    if not segments:
+        return last_speech_timestamp
+    per_segment = [[t for t in seg["tokens"] if t < eot] for seg in segments]
+    durations = np.array([w.end - w.start for w in alignment])
+    durations = durations[durations.nonzero()]
+    median = min(0.7, float(np.median(durations))) if len(durations) else 0.0
+    longest = 2 * median
+    if len(durations):                                                          # :299-308 long words at sentence boundaries
+        for i in range(1, len(alignment)):
+            w = alignment[i]
+            if w.end - w.start > longest:
+                if w.word in SENTENCE_END_MARKS:
+                    w.end = w.start + longest
+                elif alignment[i - 1].word in SENTENCE_END_MARKS:
+                    w.start = w.end - longest
+    merge_punctuations(alignment, prepend_punctuations, append_punctuations)
+    from .audio import HOP_LENGTH, SAMPLE_RATE
+    offset = segments[0]["seek"] * HOP_LENGTH / SAMPLE_RATE
+    k = 0
+    for seg, toks in zip(segments, per_segment):
+        words, used = [], 0
+        while k < len(alignment) and used < len(toks):                          # :317-332
+            w = alignment[k]
+            if w.word:
+                words.append({"word": w.word, "start": round(offset + w.start, 2), "end": round(offset + w.end, 2), "probability": w.probability})
+            used += len(w.tokens)
+            k += 1
+        if words:
+            first = words[0]
+            after_pause = first["end"] - last_speech_timestamp > median * 4     # :338-352 first words after a pause
+            too_long = first["end"] - first["start"] > longest or (len(words) > 1 and words[1]["end"] - first["start"] > longest * 2)
+            if after_pause and too_long:
+                if len(words) > 1 and words[1]["end"] - words[1]["start"] > longest:
+                    cut = max(words[1]["end"] / 2, words[1]["end"] - longest)
+                    first["end"] = words[1]["start"] = cut
+                first["start"] = max(0, first["end"] - longest)
+            if seg["start"] < first["end"] and seg["start"] - 0.5 > first["start"]:      # :355-363 segment start vs first word
+                first["start"] = max(0, min(first["end"] - median, seg["start"]))
+            else:
+                seg["start"] = first["start"]
+            last = words[-1]
+            if seg["end"] > last["start"] and seg["end"] + 0.5 < last["end"]:   # :366-374 segment end vs last word
+                last["end"] = max(last["start"] + median, seg["end"])
+            else:
+                seg["end"] = last["end"]
+            last_speech_timestamp = seg["end"]
+        seg["words"] = words
+    return last_speech_timestamp
