@@ -3,6 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W            # this framework on N B200s (torchrun for N > 1)
     python bench.py --impl reference --steps K --warmup W    # the reference's PyTorch CPU path (oracle port) on host cores
+    python bench.py --shard-file 60 --model large-v3 [--gpus N]   # BASELINE configs[4]: ONE long file, windows sharded r::N
 
 One step = transcribe one 1-minute synthetic clip (2 fixed 30-s windows; BASELINE.json configs[3]) per GPU:
 log-mel -> encoder -> crossKV -> decoder256 -> <=223 decoder1 steps with on-device beam search.  Multi-GPU is
@@ -42,6 +43,9 @@ def parse():
     ap.add_argument("--cpu-baseline", type=int, default=1, help="time the oracle port on host cores (N=1 only)")
     ap.add_argument("--long-clip", type=float, default=4.0, help="minutes of a second, longer clip reported as long_clip (0 = skip; N=1 only)")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--shard-file", type=float, default=0.0,
+                    help="minutes of ONE synthetic file whose fixed windows are sharded rank::world_size (BASELINE configs[4]; strong scaling)")
+    ap.add_argument("--word-timestamps-pass", type=int, default=1, help="also time the workload with word_timestamps=True (N=1 only)")
     return ap.parse_args()
 
 
@@ -76,10 +80,45 @@ def encoder_flops(dims) -> float:
     return 2 * 3000 * 3 * m * d + 2 * 1500 * 3 * d * d + le * (24 * 1500 * d * d + 4 * 1500 * 1500 * d)
 
 
-def decoder1_bytes(dims, bs: int, t: float) -> float:
+def decoder1_bytes(dims, bs: int, t: float, windows: int = 1) -> float:
+    """SURVEY 8d for ONE launch of the step kernel that advances `windows` windows: the weights once, everything else per window"""
     d, ld, v = dims.n_text_state, dims.n_text_layer, dims.n_vocab
-    return (2 * (ld * (14 * d * d + 16 * d) + 2 * d + v * d) + 4 * ld * 1500 * d + 4 * ld * bs * (t + 1) * d
-            + 4 * ld * bs * d + 4 * bs * d + 4 * bs * v)
+    weights = 2 * (ld * (14 * d * d + 16 * d) + 2 * d + v * d)
+    per_window = 4 * ld * 1500 * d + 4 * ld * bs * (t + 1) * d + 4 * ld * bs * d + 4 * bs * d + 4 * bs * v
+    return weights + windows * per_window
+
+
+def lane_plan(n_windows: int, nb: int):
+    """(lanes, windows per lane) of b200DecodeWindows for one batch of windows (csrc/api_batch.cu: decode_windows_batch)"""
+    lanes = min(int(os.environ.get("B200_DECODE_LANES", "8")), 8, n_windows)
+    per_lane = min(int(os.environ.get("B200_BATCH_WINDOWS", "8")), max(1, 40 // nb), -(-n_windows // lanes))
+    return lanes, per_lane
+
+
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from this round's committed ncu capture
+    (profiles/r2_<kernel>_ncu_full.csv, written by tools/ncu_summaries.py), or None"""
+    import csv
+    path = os.path.join(ROOT, "profiles", f"r2_{kernel}_ncu_full.csv")
+    if not os.path.exists(path):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    with open(path, newline="") as f:
+        rows = [r for r in csv.reader(f) if r and not r[0].startswith("#")]
+    if len(rows) < 2:
+        return None
+    hdr = rows[0]
+    total, n = 0.0, 0
+    for r in rows[1:]:
+        t = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            col = next((i for i, h in enumerate(hdr) if h.startswith(name + " [")), None)
+            if col is None:
+                return None
+            t += float(r[col].replace(",", "")) * scale.get(hdr[col].split("[")[1].rstrip("]"), 1.0)
+        total += t
+        n += 1
+    return total / n if n else None
 
 
 class ClockSampler(threading.Thread):
@@ -180,24 +219,31 @@ def main():
                 f"condition_on_previous_text=False, temperature 0")
     config = {"workload": workload, "windows_per_step_per_gpu": n_windows, "beam_size": a.beam, "sample_len": a.sample_len,
               "word_timestamps": bool(a.word_timestamps), "l2": "working set (>2 GB of weights per step) exceeds the 126 MB L2",
-              "decode_lanes": "independent windows decode concurrently, one lane per window up to 8 (B200_DECODE_LANES)"}
+              "decode_lanes": "windows are spread over up to 8 concurrent decode lanes (B200_DECODE_LANES); a lane advances its windows in "
+                              "one batched step kernel (one window per lane up to 8 windows per batch)"}
 
     if a.impl == "reference":
         if rank != 0:
             return
         _, _, ckpt_path = weights_folder(a.model, a.seed)
-        vals = []
+        vals, walls = [], []
+        cap = min(25, a.sample_len)                                      # bounded sample: 24 decoder1 steps of one window per step
         for i in range(a.warmup + a.steps):
-            r = cpu_reference(dims, ckpt_path, dims.n_mels, a.sample_len, a.beam, min(65, a.sample_len), audio_seconds, n_windows)
+            t0 = time.perf_counter()
+            r = cpu_reference(dims, ckpt_path, dims.n_mels, a.sample_len, a.beam, cap, audio_seconds, n_windows)
             if i >= a.warmup:
                 vals.append(r)
+                walls.append(time.perf_counter() - t0)
         v = statistics.mean(x["rtfx"] for x in vals)
         last = vals[-1]
-        sample = (f"1 of {n_windows} windows per step: mel + encoder + crossKV + decoder256 x{a.beam} + {last['steps_timed']-1} decoder1 "
-                  f"steps + beam search, fp32 torch CPU; decoder extrapolated to {last['steps_extrapolated']} steps, clip to {n_windows} windows")
+        sample = (f"per step 1 of {n_windows} windows: mel + encoder + crossKV + decoder256 x{a.beam} + {last['steps_timed']-1} decoder1 "
+                  f"steps + beam search, fp32 torch CPU (oracle port of the reference's use_coreml=False path); RTFx extrapolates the "
+                  f"measured per-step decoder time to {last['steps_extrapolated']} steps and the window to {n_windows} windows; "
+                  f"ms_per_step is the wall time of the sample actually run")
         print(json.dumps({"impl": "reference", "metric": "rtfx", "value": v, "unit": "audio_s/wall_s", "n_gpus": a.gpus,
-                          "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000 * audio_seconds / v, "higher_is_better": True,
+                          "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000 * statistics.mean(walls), "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "extrapolated": True,
                           "cpu_baseline": {"value": v, "unit": "audio_s/wall_s", "cores": last["cores"], "kind": "port", "sample": sample,
                                            "detail": {k: last[k] for k in ("t_mel_s", "t_encoder_s", "t_prefill_s", "t_step_s")}},
                           "e2e": {"value": v, "unit": "audio_s/wall_s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -229,6 +275,51 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if a.shard_file > 0:
+        # BASELINE configs[4]: ONE long file, its fixed 30-s windows sharded rank::world_size (whisper/transcribe.py:276-290 loops the
+        # windows of a file); strong scaling: the file is the same at every N.  value = file seconds / max-over-ranks device time.
+        from whisper_b200.transcribe import gather_sharded
+        n_file = int(a.shard_file * 60 * 16000)
+        file_host = synth.noise_audio(1, n_file).pin_memory()            # every rank holds the whole file (the log-mel needs its global max)
+        file_dev = file_host.cuda()
+        skw = dict(kw, rank=rank, world_size=world)
+        for _ in range(max(a.warmup, 1)):
+            transcribe(model, file_dev, **skw)
+        vals = {}
+        for name, src in (("dev", file_dev), ("e2e", file_host)):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            model.stage_times_ms(reset=True)
+            e0.record()
+            for _ in range(a.steps):
+                res = transcribe(model, src, **skw)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            vals[name] = float(t[0])
+        merged = gather_sharded(res, world)
+        stages = model.stage_times_ms()
+        if rank == 0:
+            total_windows = (n_file + 480000 - 1) // 480000
+            assert merged["windows"] == total_windows, (merged["windows"], total_windows)
+            secs = n_file / 16000.0
+            print(json.dumps({"metric": "rtfx", "value": secs * a.steps / (vals["dev"] / 1000.0), "unit": "audio_s/wall_s", "n_gpus": world,
+                              "steps": a.steps, "warmup": a.warmup, "ms_per_step": vals["dev"] / a.steps, "higher_is_better": True,
+                              "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                              "config": {"workload": f"{a.model} dims random-init, beam_size={a.beam}, ONE {a.shard_file:g}-min synthetic file = "
+                                                     f"{total_windows} fixed 30-s windows sharded rank::world_size over {world} GPU(s) "
+                                                     f"(BASELINE configs[4]), sample_len={a.sample_len}", "windows": total_windows,
+                                         "windows_rank0": res["windows"], "window_batch": a.window_batch},
+                              "e2e": {"value": secs * a.steps / (vals["e2e"] / 1000.0), "unit": "audio_s/wall_s",
+                                      "h2d_bytes_per_step": 4 * n_file, "d2h_bytes_per_step": res["windows"] * (max(a.beam, 1) * 449 * 4 + 44)},
+                              "stage_ms_per_step_rank0": {k: v / a.steps for k, v in stages.items()},
+                              "segments": len(merged["segments"]), "tokens": sum(len(s["tokens"]) for s in merged["segments"])}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     def timed(audio, steps):
         barrier()
@@ -270,25 +361,29 @@ def main():
                    "d2h_bytes_per_step": n_windows * (max(a.beam, 1) * 449 * 4 + max(a.beam, 1) * 8 + 4)},
            "gpu_launches": int(launches), "clocks": sampler.summary(), "tokens_per_step": n_tok,
            "stage_ms_per_step": {k: v / a.steps for k, v in stages.items()}}
-    # decoder1 roofline: device time of the step loop / decoder1 steps executed (each result.steps includes the prefill step)
+    # decoder1 roofline: one launch of decoder_batch_kernel advances the windows of one lane by one token.  achieved = algorithmic
+    # bytes of a launch (the weights once + per window cross K/V, self K/V, I/O) x launches / CUDA-event time of the
+    # whole decoder1 loop (sampling kernels and launch gaps included; the lanes run concurrently, so this is their aggregate rate)
     dec_steps = sum(max(x - 1, 0) for x in res["decode_steps"])
     if dec_steps:
-        per_step_ms = stages["decoder1"] / a.steps / dec_steps
+        nb = max(a.beam, 1)
+        lanes, per_lane = lane_plan(min(n_windows, a.window_batch), nb)
+        per_step_ms = stages["decoder1"] / a.steps / dec_steps           # per window-step
         n_init = len(model.specials.sot_sequence)
         t_mean = sum(n_init + (x - 1) / 2.0 for x in res["decode_steps"]) / len(res["decode_steps"])
-        by = decoder1_bytes(dims, max(a.beam, 1), t_mean)
-        ach = by / (per_step_ms * 1e-3) / 1e9
-        lanes = min(int(os.environ.get("B200_DECODE_LANES", "8")), 8, n_windows)
-        out["roofline"] = {"kernel": "decoder_mega_kernel: one persistent launch per decoder1 token step (LN + 7 GEMVs per layer, self / "
-                                     "cross attention, vocabulary projection) + the sampling kernel that follows it",
+        by_launch = decoder1_bytes(dims, nb, t_mean, per_lane)
+        ach = by_launch / per_lane / (per_step_ms * 1e-3) / 1e9
+        out["roofline"] = {"kernel": "decoder_batch_kernel: one persistent launch per decoder1 token step of a lane (LN + 7 GEMVs per layer, "
+                                     "self / cross attention, vocabulary projection for every window x beam row of the lane) + the "
+                                     "sampling kernel that follows it",
                            "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                           # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_decoder_mega_r1g_ncu_full.csv (t ~ 10)
-                           "traffic": 354.0e6,
-                           "peak_source": which, "bytes_per_step": by, "us_per_step": per_step_ms * 1e3, "steps": dec_steps,
-                           "lanes": lanes,
-                           "note": f"algorithmic bytes of one token step of one window (SURVEY 8d formula at the mean text_offset) divided by "
-                                   f"the CUDA-event time of the whole decoder1 loop per window-step, sampling kernels and launch gaps included; "
-                                   f"{lanes} windows decode concurrently on disjoint SM halves, so this is the aggregate rate of {lanes} step kernels"}
+                           "traffic": ncu_traffic("decoder_batch"),
+                           "peak_source": which, "bytes_per_launch": by_launch, "windows_per_launch": per_lane, "lanes": lanes,
+                           "us_per_window_step": per_step_ms * 1e3, "us_per_step": per_step_ms * 1e3, "steps": dec_steps,
+                           "note": f"algorithmic bytes of one launch (weights once + {per_lane} window(s) of cross K/V, self K/V and I/O at the "
+                                   f"mean text_offset) per window, divided by the CUDA-event time of the decoder1 loop per window-step; "
+                                   f"{lanes} lane(s) run concurrently on {lanes} disjoint SM groups, so this is their aggregate HBM rate; "
+                                   f"traffic = dram bytes of ONE launch from profiles/r2_decoder_batch_ncu_full.csv (null if absent)"}
     enc_ms = stages["encoder"] / a.steps / n_windows
     if enc_ms > 0:
         fl = encoder_flops(dims)
@@ -299,12 +394,13 @@ def main():
         # the same path on a longer clip: more independent windows -> more concurrent decode lanes (not the headline workload)
         nl = int(a.long_clip * 60 * 16000)
         long_audio = synth.noise_audio(101, nl).cuda()
-        transcribe(model, long_audio, **kw)
+        for _ in range(2):                                   # (the second pass captures the encoder graph of this window count)
+            transcribe(model, long_audio, **kw)
         ms_l, _, res_l, _, st_l = timed(long_audio, 2)
         wl = (nl + 480000 - 1) // 480000
         ds = sum(max(x - 1, 0) for x in res_l["decode_steps"])
         t_mean_l = sum(len(model.specials.sot_sequence) + (x - 1) / 2.0 for x in res_l["decode_steps"]) / len(res_l["decode_steps"])
-        by_l = decoder1_bytes(dims, max(a.beam, 1), t_mean_l)
+        by_l = decoder1_bytes(dims, max(a.beam, 1), t_mean_l, 1)
         ach_l = by_l / (st_l["decoder1"] / 2 / ds * 1e-3) / 1e9 if ds else 0.0
         out["long_clip"] = {"minutes": a.long_clip, "windows_per_step": wl, "decode_lanes": min(8, wl), "value": (nl / 16000.0) * 2 / (ms_l / 1000.0),
                             "unit": "audio_s/wall_s", "ms_per_step": ms_l / 2,
@@ -312,6 +408,19 @@ def main():
                             "encoder_tflops": encoder_flops(dims) / (st_l["encoder"] / 2 / wl * 1e-3) / 1e12,
                             "note": "same transcribe() call on a longer clip (window_batch 8): algorithmic decoder1 bytes per window-step / "
                                     "CUDA-event time of the decoder1 loop per window-step, aggregate over the concurrent lanes"}
+    if world == 1 and a.word_timestamps_pass and not a.word_timestamps:
+        # the same workload with word_timestamps=True (cross-attention of the alignment heads, median filter, DTW per window)
+        kw_w = dict(kw, word_timestamps=True)
+        transcribe(model, audio_dev, **kw_w)
+        kw_saved = dict(kw)
+        kw.update(kw_w)
+        ms_w, _, res_w, _, st_w = timed(audio_dev, max(2, a.steps // 2))
+        kw.clear(); kw.update(kw_saved)
+        n_w = max(2, a.steps // 2)
+        out["word_timestamps"] = {"value": audio_seconds * n_w / (ms_w / 1000.0), "unit": "audio_s/wall_s", "ms_per_step": ms_w / n_w,
+                                  "stage_ms_per_step": {k: v / n_w for k, v in st_w.items()},
+                                  "words": sum(len(s.get("words", [])) for s in res_w["segments"]),
+                                  "relative_to_value": (audio_seconds * n_w / (ms_w / 1000.0)) / value}
     if a.cpu_baseline and world == 1:
         r = cpu_reference(dims, ckpt_path, dims.n_mels, a.sample_len, a.beam, a.sample_len, audio_seconds, n_windows)   # ~10 s: one full window
         out["cpu_baseline"] = {"value": r["rtfx"], "unit": "audio_s/wall_s", "cores": r["cores"], "kind": "port",

@@ -1,6 +1,7 @@
 // C ABI of libwhisper_b200.so, Part 1: the plugin surface of wangchou/whisper.coreml
 // (coreml/coreml.h:5-31, bodies coreml/coreml.mm) re-implemented on sm_100a.
 #include <string.h>
+#include <map>
 
 #include <stdlib.h>
 
@@ -16,6 +17,7 @@ int take_errors(char*, int);
 void gemm_clear_map_cache();
 void attention_clear_map_cache();
 void decode_clear_graphs();
+void encoder_clear_graphs();
 
 State& S() { static State s; return s; }
 
@@ -47,7 +49,7 @@ bool ensure_encoder_capacity(int W) {
     dev_free(&s.xa);
     s.xa = new_xa;
     ok &= dev_alloc(&s.d_seeks, (size_t)W);
-    gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
+    gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs(); encoder_clear_graphs();
     if (ok) s.w_cap = W;
     return ok;
 }
@@ -58,11 +60,58 @@ static GemmParams lin(const bf16* A, int M, int K, const bf16* W, const float* b
     return p;
 }
 
+// Everything behind mel_to_rows reads and writes the encoder's own workspaces only, so the ~290 launches of a batch of W windows
+// are captured once per W (after one eager pass that creates the tensor maps and sets the kernel attributes) and replayed as a
+// CUDA graph: the kernels are 9 - 60 us long and the gaps between dependent launches add up (B200_ENCODER_GRAPH=0 turns it off).
+struct EncGraph { cudaGraphExec_t exec = nullptr; long launches = 0; bool seen = false; };
+static std::map<int, EncGraph> g_enc_graphs;
+void encoder_clear_graphs() {
+    for (auto& kv : g_enc_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    g_enc_graphs.clear();
+}
+static void encoder_layers(int W);
+
 void run_encoder(const float* d_mel, long total_frames, long valid_frames, int W) {
+    State& s = S();
+    cudaStream_t st = s.stream;
+    mel_to_rows(d_mel, total_frames, valid_frames, s.d_seeks, W, s.n_mels, s.cpad, s.melrows, st);
+    static const bool use_graph = !(getenv("B200_ENCODER_GRAPH") && atoi(getenv("B200_ENCODER_GRAPH")) == 0);
+    EncGraph& g = g_enc_graphs[W];
+    if (use_graph && g.exec) {
+        B200_CHECK(cudaGraphLaunch(g.exec, st));
+        g_launch_count += g.launches;
+    } else if (use_graph && g.seen) {
+        cudaGraph_t graph = nullptr;
+        const long l0 = g_launch_count;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            encoder_layers(W);
+            g.launches = g_launch_count - l0;
+            if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+                g_launch_count = l0;
+                B200_CHECK(cudaGraphLaunch(g.exec, st));
+                g_launch_count += g.launches;
+            } else {
+                cudaGetLastError();
+                g.exec = nullptr;
+                g_launch_count = l0;
+                encoder_layers(W);
+            }
+            if (graph) cudaGraphDestroy(graph);
+        } else {
+            cudaGetLastError();
+            encoder_layers(W);
+        }
+    } else {
+        encoder_layers(W);
+        g.seen = true;
+    }
+    s.n_windows = W;
+}
+
+static void encoder_layers(int W) {
     State& s = S();
     const int d = s.d, M = W * N_AUDIO_CTX;
     cudaStream_t st = s.stream;
-    mel_to_rows(d_mel, total_frames, valid_frames, s.d_seeks, W, s.n_mels, s.cpad, s.melrows, st);
     {   // conv1 (k3, p1) + GELU: three accumulating passes over row-shifted views (encoder.py:124)
         GemmParams p{};
         for (int k = 0; k < 3; ++k) p.A[k] = s.melrows + (size_t)k * s.cpad;
@@ -105,7 +154,6 @@ void run_encoder(const float* d_mel, long total_frames, long valid_frames, int W
         gemm_tcgen05(p2, st);
     }
     layernorm(s.x, s.ln_post_w, s.ln_post_b, 1e-7f, s.xa, nullptr, M, d, st);   // encoder.py:133-134
-    s.n_windows = W;
 }
 
 // =================================================================================================
@@ -117,7 +165,7 @@ void run_cross_kv(int W) {
         if (!dev_alloc(&s.ckv, (size_t)W * s.ckv_window_elems())) return;
         if (!dev_alloc(&s.ckv_frag, (size_t)W * s.ckv_frag_window_elems(), true)) return;   // pad keys 1500..1503 stay zero
         s.ckv_cap = W;
-        gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
+        gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs(); encoder_clear_graphs();
     }
     const int d = s.d;
     GemmParams p{};
@@ -180,11 +228,14 @@ void run_prefill(int beam_idx, bool want_chw, int rows) {
         c.ldk = c.ldv = 64; c.k_head_stride = c.v_head_stride = (long)N_AUDIO_CTX * 64;
         c.O = s.patt; c.ldo = d; c.o_head_stride = 64;
         c.n_q = M; c.n_k = N_AUDIO_CTX; c.n_head = s.H; c.batch = 1;
-        if (want_chw && s.n_align > 0) {                                // raw QK of the alignment heads (decoder.py:306-308)
+        // no mask: the 256 x 1500 cross-attention runs on the tensor cores (tcgen05 flash attention); the raw QK of the alignment
+        // heads (decoder.py:306-308) comes from a small kernel of its own
+        attention_tc(c, st);
+        if (want_chw && s.n_align > 0) {
             c.qk_dump = s.pchw; c.dump_slot = s.d_dump_slot + l * s.H; c.dump_ld = N_AUDIO_CTX;
             c.dump_slot_stride = (long)PREFILL_CTX * N_AUDIO_CTX;
+            attention_qk_dump(c, st);
         }
-        attention_simt(c, st);
         GemmParams pc = lin(s.patt, M, d, L.cross_out.w, L.cross_out.b, d, s.px, true);
         pc.add = s.px; pc.add_rows = M; pc.ld_add = d;
         gemm_tcgen05(pc, st);
@@ -329,7 +380,7 @@ void closeEncoder() {
     dev_free(&s.melrows); dev_free(&s.h1); dev_free(&s.x); dev_free(&s.y); dev_free(&s.qkv); dev_free(&s.att);
     dev_free(&s.hid); dev_free(&s.xa); dev_free(&s.mel_stage); dev_free(&s.d_seeks);
     s.enc_w.unload(); s.enc_layers.clear(); s.w_cap = 0; s.n_windows = 0; s.enc_loaded = false;
-    gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
+    gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs(); encoder_clear_graphs();
 }
 
 void encoderPredict(float* melSegment) {
@@ -364,7 +415,7 @@ void closeCrossKV() {
     use_device();
     B200_CHECK(cudaDeviceSynchronize());
     dev_free(&s.ckv); dev_free(&s.ckv_frag); s.ckv_cap = 0; s.ckv_w.unload(); s.ckv_loaded = false;
-    gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
+    gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs(); encoder_clear_graphs();
 }
 
 void crossKVPredict() {
@@ -409,7 +460,7 @@ void closeDecoder256() {
     release_decoder_weights();
     s.align_heads.clear();             // a model loaded next starts from the default alignment heads (model.py:55-58), not this one's
     s.dec256_loaded = false;
-    gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs();
+    gemm_clear_map_cache(); attention_clear_map_cache(); decode_clear_graphs(); encoder_clear_graphs();
 }
 
 void decoder256Predict(float* x, float* qk_mask, float* out_x, float* out_cross_head_weights, int beam_idx) {

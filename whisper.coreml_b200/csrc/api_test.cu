@@ -20,7 +20,8 @@ extern "C" void b200TestGemm(const void* dA, const void* dB, const float* dBias,
 }
 
 namespace b200 { extern int g_gemm_force; }
-extern "C" void b200TestGemmTile(int sel) { b200::g_gemm_force = sel; }
+namespace b200 { void encoder_clear_graphs(); }
+extern "C" void b200TestGemmTile(int sel) { b200::g_gemm_force = sel; b200::encoder_clear_graphs(); }    // (a captured encoder graph holds the old tile choice)
 
 // average device time (ms, CUDA events around `iters` back-to-back launches) of one GEMM configuration;
 // mode bits: 1 = bias, 2 = GELU, 4 = fp32 output with an fp32 residual added (else bf16 output)

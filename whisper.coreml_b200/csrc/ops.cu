@@ -215,6 +215,59 @@ __global__ void __launch_bounds__(SA_Q) attention_simt_kernel(const AttnParams p
     }
 }
 
+// Raw (pre-softmax) QK of the heads that have a dump slot - the alignment heads of the word-timestamp pass
+// (decoder.py:306-308) - as its own small kernel, so that the attention itself can run on the tensor cores (attention_tc has
+// no dump path): 64 keys x 32 queries per CTA, K and Q tiles as fp32 in shared memory, 8 outputs per thread.
+__global__ void __launch_bounds__(256) attention_qk_dump_kernel(const AttnParams p) {
+    const int h = blockIdx.z;
+    const int slot = p.dump_slot[h];
+    if (slot < 0) return;
+    __shared__ float sk[64][65];
+    __shared__ float sq[32][64];
+    const int j0 = blockIdx.x * 64, i0 = blockIdx.y * 32, tid = threadIdx.x;
+    const bf16* kb = p.K + h * p.k_head_stride;
+    const bf16* qb = p.Q + h * p.q_head_stride;
+    for (int e = tid; e < 64 * 8; e += 256) {                     // 8 x 16-byte pieces per key row
+        const int jj = e >> 3, c = (e & 7) * 8;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (j0 + jj < p.n_k) u = *reinterpret_cast<const uint4*>(kb + (long)(j0 + jj) * p.ldk + c);
+        float* dk = &sk[jj][c];
+        dk[0] = bf16lo(u.x); dk[1] = bf16hi(u.x); dk[2] = bf16lo(u.y); dk[3] = bf16hi(u.y);
+        dk[4] = bf16lo(u.z); dk[5] = bf16hi(u.z); dk[6] = bf16lo(u.w); dk[7] = bf16hi(u.w);
+    }
+    {
+        const int ii = tid >> 3, c = (tid & 7) * 8;                // 32 query rows x 8 pieces = 256 threads
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (i0 + ii < p.n_q) u = *reinterpret_cast<const uint4*>(qb + (long)(i0 + ii) * p.ldq + c);
+        float* dq = &sq[ii][c];
+        dq[0] = bf16lo(u.x); dq[1] = bf16hi(u.x); dq[2] = bf16lo(u.y); dq[3] = bf16hi(u.y);
+        dq[4] = bf16lo(u.z); dq[5] = bf16hi(u.z); dq[6] = bf16lo(u.w); dq[7] = bf16hi(u.w);
+    }
+    __syncthreads();
+    const int j = tid & 63, qg = tid >> 6;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) {
+        const float kv = sk[j][c];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = fmaf(sq[qg * 8 + q][c], kv, acc[q]);
+    }
+    if (j0 + j < p.n_k) {
+        float* dump = p.qk_dump + (long)slot * p.dump_slot_stride + j0 + j;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = i0 + qg * 8 + q;
+            if (i < p.n_q) dump[(long)i * p.dump_ld] = acc[q];
+        }
+    }
+}
+
+void attention_qk_dump(const AttnParams& p, cudaStream_t s) {
+    dim3 grid(cdiv(p.n_k, 64), cdiv(p.n_q, 32), p.n_head);
+    attention_qk_dump_kernel<<<grid, 256, 0, s>>>(p);
+    B200_LAUNCH_CHECK();
+}
+
 void attention_simt(const AttnParams& p, cudaStream_t s) {
     dim3 grid(cdiv(p.n_q, SA_Q), p.n_head, p.batch);
     attention_simt_kernel<<<grid, SA_Q, 0, s>>>(p);

@@ -30,5 +30,6 @@ struct AttnParams {
 // (encoder.py:38) or into the query weights (decoder.py:16-20), and so does the exporter.
 void attention_tc(const AttnParams& p, cudaStream_t s);      // tcgen05 flash attention (attention.cu)
 void attention_simt(const AttnParams& p, cudaStream_t s);    // general SIMT kernel (masks, QK dump)
+void attention_qk_dump(const AttnParams& p, cudaStream_t s); // raw QK of the heads with a dump slot only (batch 1)
 
 }  // namespace b200
