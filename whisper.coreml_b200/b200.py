@@ -186,6 +186,12 @@ class B200:
         startT = timer()
         x = x.to(torch.float32).contiguous()
         qk_mask = qk_mask.to(torch.float32).contiguous()
+        # the library reads bs rows of x (the beam slots given to loadDecoder256, coreml.mm:230) and a (1, 449) mask, (1, 450) for bs == 1
+        if x.numel() != self.bs * self.n_state:
+            raise ValueError(f"decoder1Predict expects x of shape ({self.bs}, 1, {self.n_state}) - the decoder was loaded with "
+                             f"{self.bs} beam slots - got {tuple(x.shape)}")
+        if qk_mask.numel() != (450 if self.bs == 1 else 449):
+            raise ValueError(f"decoder1Predict expects a qk_mask of {450 if self.bs == 1 else 449} elements, got {qk_mask.numel()}")
         self.obj.decoder1Predict(_ptr(x), _ptr(qk_mask), int(text_offset), _ptr(self.out_x1))
         _lib.check_errors("decoder1Predict")
         if logPredictTime:

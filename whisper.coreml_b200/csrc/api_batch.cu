@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <map>
+#include <string>
 #include <vector>
 
 #include "api_batch.cuh"
@@ -51,6 +52,26 @@ void batch_clear_graphs() {
     g_batch_graphs.clear();
 }
 
+// A bounded wait of the step kernel gave up (protocol bug or a dead peer CTA): log which wait and how far every CTA of every lane got.
+static void report_step_fault(unsigned long long f) {
+    static bool reported = false;
+    if (reported) return;
+    reported = true;
+    record_error("decoder_batch_kernel gave up in wait %d: CTA %d of %d, thread %d", (int)(f >> 48 & 0x7fff), (int)(f >> 16 & 0xffff),
+                 (int)(f >> 32 & 0xffff), (int)(f & 0xffff));
+    const unsigned* p = db_fault_progress();
+    for (int lane = 0; p && lane < 8; ++lane) {
+        std::string line;
+        char buf[48];
+        for (int c = 0; c < DB_PROGRESS_LD; ++c) {
+            const unsigned v = p[lane * DB_PROGRESS_LD + c];
+            if (!v) continue;
+            snprintf(buf, sizeof buf, " %d:%d/%d", c, (int)(v & 0xffff) - 1, (int)(v >> 16) - 1);
+            line += buf;
+        }
+        if (!line.empty()) fprintf(stderr, "[whisper_b200] lane %d progress (CTA:consumer stage/producer stage):%s\n", lane, line.c_str());
+    }
+}
 void batch_set_model(const DbModel& m) { g_db_model_set = true; db_set_model(m); batch_clear_graphs(); }
 
 static void lane_free(BatchCtx& c, bool is_lane0) {
@@ -211,7 +232,7 @@ static DbArgs step_args(const BatchJob& j, bool prompt, int text_offset) {
     State& s = S();
     BatchCtx& c = g_lane[j.lane];
     DbArgs a{};
-    a.W = j.W; a.nbw = prompt ? 1 : j.nb; a.slot_stride = j.nb;
+    a.W = j.W; a.nbw = prompt ? 1 : j.nb; a.slot_stride = j.nb; a.lane_id = j.lane;
     for (int w = 0; w < j.W; ++w) a.win[w] = j.windows[w];
     a.ckv_frag = s.ckv_frag; a.ckv_window_elems = (long)s.ckv_frag_window_elems();
     fill_geometry(a, a.W * a.nbw);
@@ -417,6 +438,8 @@ int decode_windows_batch(const int* windows, int n_windows, const int* initial_t
             B200_CHECK(cudaMemcpyAsync(tok.data(), c.tokens, tok.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
             B200_CHECK(cudaMemcpyAsync(fin.data(), c.fin_tokens, fin.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
             B200_CHECK(cudaStreamSynchronize(c.stream));
+            if (const unsigned long long f = db_fault_word())
+                report_step_fault(f);
             for (int q = 0; q < j.W; ++q) {
                 const size_t o = (size_t)(j.w0 + q);
                 const int n = emit_window(hs[q], tok.data() + (size_t)q * nb * DEC_TOK_LD, fin.data() + (size_t)q * DEC_MAX_BEAMS * DEC_TOK_LD, nb, n_initial,

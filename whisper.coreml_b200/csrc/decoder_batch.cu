@@ -26,9 +26,23 @@
 // activation copies) halves, which is where a step's time goes (tools/step_timeline.py), and nothing needs to be batched
 // by hand in asm to stay inside the register budget.  LayerNorm rows are staged as the bf16 pairs they arrive as and
 // normalised in place; the MLP hidden row (4d columns) is consumed in K chunks of xs_cols columns so that 40 rows fit.
+//
+// Ring protocol.  full[slot] (1 arrival + tx bytes) / empty[slot] (4 arrivals) mbarriers; a wait names only the PARITY of the
+// use it waits for, so a waiter must never be a whole ring cycle away from the barrier in either direction:
+//   * whoever waits on a slot either releases it itself (GEMV tile group: 4 warps wait, 4 warps arrive) or passes a CTA-wide
+//     barrier before the release (LayerNorm gamma | beta, cross-attention keys); warps that do not read a slot do not wait
+//     on it (cross-attention values) - a late waiter would otherwise find the slot released, refilled, and the parity back
+//     where it started, and wait forever;
+//   * the two GEMV tile groups skip each other's slots without waiting, so the previous use of a group's slot may be one it
+//     never watched: before its own wait it checks seen[slot] (the use index the last waiter observed complete) - otherwise
+//     a wait issued while the previous use is still in flight passes at once, on stale bytes, and its release corrupts the
+//     empty barrier's count (the large-v3 hang: 18-CTA lanes, 4-slot MLP2 tiles).
+// Every bounded wait that gives up stores {where, CTA, thread} and the per-CTA stage table in a host-mapped word before the
+// trap (db_fault_word), so a protocol bug reads as a log line instead of a hung box.
 #include "decoder_batch.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace b200 {
 
@@ -54,9 +68,9 @@ struct DbCfg {
     static constexpr int PASSES = (ROWS * 16 + GT - 1) / GT;          // epilogue passes: one (row, output) per group thread and pass
     static constexpr int RED_FLOATS = 2 * GW * NT * 128;              // one reduction buffer per tile group
 };
-// scratch behind the activation rows, in floats: red | sp | sq | stat | rowstat | ints (spos[8] stok[40]) | barriers
+// scratch behind the activation rows, in floats: red | sp | sq | stat | rowstat | ints (spos[8] stok[40]) | barriers | stage descriptors | seen[4]
 __host__ __device__ constexpr size_t db_scratch_bytes(int nt, int cw) {
-    return ((size_t)2 * 4 * nt * 128 + 8 * DB_SPLIT_KEYS + 8 * 64 + 64 + 2 * DB_MAX_ROWS + 48) * 4 + 2 * DB_MAX_SLOTS * 8 + 2 * 64;
+    return ((size_t)2 * 4 * nt * 128 + 8 * DB_SPLIT_KEYS + 8 * 64 + 64 + 2 * DB_MAX_ROWS + 48) * 4 + 2 * DB_MAX_SLOTS * 8 + 2 * 64 + DB_MAX_SLOTS * 4;
 }
 
 __device__ __forceinline__ void db_mma(float (&d)[4], const uint4& lo, const uint4& hi, const uint4& xb) {
@@ -81,10 +95,39 @@ __device__ __forceinline__ void db_cp_async_wait_all() { asm volatile("cp.async.
 
 // A protocol bug traps (-> launch error) instead of hanging the GPU box.  One instruction: the kernel is instruction-fetch
 // bound (every stage's code runs once per layer from a cold instruction cache), so nothing cold may sit between hot code.
-__device__ __forceinline__ void db_timeout(int) { asm volatile("trap;"); }
-__device__ __forceinline__ void db_wait(uint64_t* bar, uint32_t parity) {         // bounded mbarrier wait
+// Before the trap the wait that gave up leaves {where, CTA, thread, grid} in a host-mapped word (db_fault_word) for the error log.
+__device__ unsigned long long* g_db_fault = nullptr;
+// Every CTA also keeps its progress (stage index + 1 of its consumers, of its producer) in g_db_progress[decode lane][CTA]; the
+// wait that gives up copies the table behind the fault word, so the log shows which CTA the others were waiting for.
+__device__ unsigned g_db_progress[DB_PROGRESS_WORDS];
+__device__ __forceinline__ void db_progress(int lane_id, int half, int it) {
+    reinterpret_cast<volatile unsigned short*>(g_db_progress + lane_id * DB_PROGRESS_LD + blockIdx.x)[half] = (unsigned short)(it + 1);
+}
+// The consumers' version is a real function (the table copy inlined at a dozen wait sites cost 2 % of the step: the kernel is
+// instruction-fetch bound); the producer's stays one store + trap, because a call reachable from BOTH role branches makes ptxas
+// drop the setmaxnreg register hand-over.
+__device__ __forceinline__ void db_fault_store(int where) {
+    *(volatile unsigned long long*)g_db_fault = 1ull << 63 | (unsigned long long)where << 48 | (unsigned long long)gridDim.x << 32 |
+                                                (unsigned long long)blockIdx.x << 16 | threadIdx.x;
+    __threadfence_system();
+}
+__device__ __noinline__ void db_timeout(int where) {
+    if (g_db_fault) {
+        volatile unsigned* dst = reinterpret_cast<volatile unsigned*>(g_db_fault + 2);
+        for (int i = 0; i < DB_PROGRESS_WORDS; ++i) dst[i] = reinterpret_cast<volatile unsigned*>(g_db_progress)[i];
+        db_fault_store(where);
+    }
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void db_timeout_producer(int where) {
+    if (g_db_fault) db_fault_store(where);
+    asm volatile("trap;");
+}
+template <bool PRODUCER = false>
+__device__ __forceinline__ void db_wait(uint64_t* bar, uint32_t parity, int where) {         // bounded mbarrier wait
     unsigned spins = 0;
-    while (!mbar_try_wait(bar, parity)) if (++spins > (1u << 24)) db_timeout(0);
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > (1u << 24)) { if (PRODUCER) db_timeout_producer(where); else db_timeout(where); }
 }
 
 __device__ __forceinline__ unsigned long long db_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
@@ -179,7 +222,8 @@ __constant__ DbModel c_db;
 struct DbRing {
     int slot; uint32_t phase;
     int n;
-    __device__ __forceinline__ void advance() { if (++slot == n) { slot = 0; phase ^= 1; } }
+    int use;                                           // running index of the slot use (consumers only)
+    __device__ __forceinline__ void advance() { ++use; if (++slot == n) { slot = 0; phase ^= 1; } }
 };
 __device__ __forceinline__ void db_range(int n_tiles, int vcta, int nctas, int& u0, int& u1) {      // tiles [u0, u1) of a GEMV stage
     u0 = vcta * n_tiles / nctas; u1 = (vcta + 1) * n_tiles / nctas;
@@ -199,8 +243,13 @@ struct DbStageSm {
 struct DbSmem {
     uint8_t* ring; bf16* xs; float* red; float* sp; float* sq; float* stat; float* rowstat; int* spos; int* stok;
     uint64_t* full; uint64_t* empty; DbStageSm* desc;
+    volatile int* seen;                                // [slot] latest use of the slot whose data some consumer has seen arrive (DbRing::use)
     int ldx;
 };
+__device__ __forceinline__ void db_seen_wait(const DbSmem& sm, const DbRing& ring) {
+    unsigned spins = 0;
+    while (sm.seen[ring.slot] < ring.use - ring.n) if (++spins > (1u << 26)) db_timeout(26);
+}
 // row r of the step -> index of its token history / slot-table row / physical KV slot
 __device__ __forceinline__ int db_trow(const DbArgs& a, int r) { const int w = r / a.nbw; return w * a.slot_stride + (r - w * a.nbw); }
 
@@ -256,6 +305,8 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, co
     for (int t = u0; t < u1; ++t) {
         const bool mine = chunked ? group == 0 : ((t - u0) & 1) == group;          // (uniform within a group)
         float add[C::PASSES];
+        // seen[] of the tile's first slot, read early (its latency hides behind the residual fetch; the value only grows)
+        int sv = mine ? sm.seen[ring.slot] : 0;
         if (mine) {
 #pragma unroll
             for (int p = 0; p < C::PASSES; ++p) {
@@ -293,7 +344,13 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, co
             if (mine) {
                 const uint4* sl = reinterpret_cast<const uint4*>(sm.ring + (size_t)ring.slot * DB_SLOT) + lane;
                 const bf16* xk = xrow + cin * 32;
-                db_wait(&sm.full[ring.slot], ring.phase);
+                // A wait knows only the PARITY of the use it waits for, and the slot's previous use may have been the other
+                // group's (skipped here without a wait): were that one still in flight, this wait would pass at once on stale
+                // bytes.  So first see that some consumer has watched the previous use arrive (db_seen_wait).
+                if (sv < ring.use - ring.n) db_seen_wait(sm, ring);
+                db_wait(&sm.full[ring.slot], ring.phase, 20);
+                if (gw == 0 && lane == 0) sm.seen[ring.slot] = ring.use;
+                sv = sm.seen[ring.slot + 1 == ring.n ? 0 : ring.slot + 1];         // the next slot of the tile
 #pragma unroll
                 for (int q0 = 0; q0 < DB_SLOT_BLOCKS / C::GW; q0 += 5) {           // two batches of five blocks per warp
                     uint4 lo[5], hi[5];
@@ -326,6 +383,9 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, co
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.empty[ring.slot]);
             }
+            // (The other group's slots are skipped without a wait: a full barrier cannot complete a second phase before its
+            // owner group has released the slot, so a group's waits on its OWN slots never alias; waiting on the other group's
+            // slots would, because the producer refills them as soon as their owner is done.)
             ring.advance();                                             // both groups track every slot of the CTA
         }
         if (!mine) continue;
@@ -391,7 +451,8 @@ __device__ __forceinline__ void db_prologue_ln(const DbSmem& sm, DbRing& ring, c
             if (tid < R) sm.stok[tid] = a.tokens[db_trow(a, tid) * DEC_TOK_LD + sm.spos[tid / a.nbw]];
             csync<C::CONS>();
         }
-        db_wait(&sm.full[ring.slot], ring.phase);                          // gamma | beta: one slot ahead of the stage's tiles
+        db_wait(&sm.full[ring.slot], ring.phase, 22);                          // gamma | beta: one slot ahead of the stage's tiles
+        if (tid == 0) sm.seen[ring.slot] = ring.use;
         const float4* gsl = reinterpret_cast<const float4*>(sm.ring + (size_t)ring.slot * DB_SLOT);
         const float inv_d = __fdividef(1.f, (float)d);
 #pragma unroll 1
@@ -505,7 +566,8 @@ __device__ __forceinline__ void db_prologue_ln(const DbSmem& sm, DbRing& ring, c
         const float inv_d = __fdividef(1.f, (float)d), mean = s1 * inv_d;
         *reinterpret_cast<float2*>(sm.rowstat + 2 * tid) = make_float2(mean, rsqrtf(fmaxf(s2 * inv_d - mean * mean, 0.f) + 1e-5f));
     }
-    db_wait(&sm.full[ring.slot], ring.phase);                              // gamma | beta: one slot ahead of the stage's tiles
+    db_wait(&sm.full[ring.slot], ring.phase, 23);                              // gamma | beta: one slot ahead of the stage's tiles
+    if (tid == 0) sm.seen[ring.slot] = ring.use;
     csync<C::CONS>();
     {
         float4 ga[C::IPR], be[C::IPR];
@@ -669,7 +731,8 @@ __device__ __forceinline__ void db_stage_cross_attn(const DbSmem& sm, DbRing& ri
         }
         csync<C::CONS>();
         // scores: one slot carries the split's key tiles (2 blocks each); warp w takes tiles w, w + CW, ...
-        db_wait(&sm.full[ring.slot], ring.phase);
+        db_wait(&sm.full[ring.slot], ring.phase, 24);
+        if (tid == 0) sm.seen[ring.slot] = ring.use;
         {
             const uint4* sl = reinterpret_cast<const uint4*>(sm.ring + (size_t)ring.slot * DB_SLOT) + lane;
             const uint4 xb0 = *reinterpret_cast<const uint4*>(sm.xs + (long)gq * sm.ldx + tq * 8);
@@ -711,8 +774,11 @@ __device__ __forceinline__ void db_stage_cross_attn(const DbSmem& sm, DbRing& ri
         // o[dim][beam] = V^T[dim][key] p[key][beam]: the slot holds the split's key blocks of the four dim tiles; warp dt owns tile dt
         const int nkc = min(DB_SPLIT_TILES / 2, n_vkc - s * (DB_SPLIT_TILES / 2));
         uint2* part = a.ll_cap + (((long)(w * H + h) * DB_N_SPLITS + s) * 8) * 66;
-        db_wait(&sm.full[ring.slot], ring.phase);
         if (warp < 4) {
+            // only the warps that read the slot (and release it) wait for it: a warp that waited without releasing could come
+            // late, after the slot has been released AND refilled, and would then wait for a parity that has come round again
+            db_wait(&sm.full[ring.slot], ring.phase, 25);
+            if (tid == 0) sm.seen[ring.slot] = ring.use;
             const uint4* sl = reinterpret_cast<const uint4*>(sm.ring + (size_t)ring.slot * DB_SLOT + (size_t)warp * nkc * 1024) + lane;
             float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
@@ -811,6 +877,7 @@ __device__ __forceinline__ DbSmem db_smem(const DbArgs& a, uint8_t* raw) {
     sm.full = reinterpret_cast<uint64_t*>(sm.stok + 40);
     sm.empty = sm.full + DB_MAX_SLOTS;
     sm.desc = reinterpret_cast<DbStageSm*>(sm.empty + DB_MAX_SLOTS);       // [2], 64 bytes each
+    sm.seen = reinterpret_cast<volatile int*>(sm.desc + 2);
     sm.ring = raw + a.ring_offset;
     return sm;
 }
@@ -827,6 +894,7 @@ __device__ __forceinline__ void db_producer(const DbArgs& a, uint8_t* raw) {
     const long head_elems = (long)64 * CROSS_KEYS_PAD;
     for (int it = 0; it < n_stages; ++it) {
         const int l = it >> 3, st = it == M.Ld * 8 ? DBS_VOCAB : (it & 7);
+        db_progress(a.lane_id, 1, it);
         if (st == DBS_SA) continue;
         if (st == DBS_CA) {
             for (int u = (cta + db_stage_rot(DBS_CA, nctas)) % nctas; u < a.W * H * DB_N_SPLITS; u += nctas) {
@@ -837,11 +905,11 @@ __device__ __forceinline__ void db_producer(const DbArgs& a, uint8_t* raw) {
                 const bf16* vf = base + (long)(l * 2 + 1) * H * head_elems + h * head_elems;
                 const int t0 = s * DB_SPLIT_TILES, nt = min(DB_SPLIT_TILES, n_ktiles - t0);
                 const int kc0 = s * (DB_SPLIT_TILES / 2), nkc = min(DB_SPLIT_TILES / 2, n_vkc - kc0);
-                db_wait(&sm.empty[ring.slot], ring.phase ^ 1);
+                db_wait<true>(&sm.empty[ring.slot], ring.phase ^ 1, 30);
                 mbar_expect_tx(&sm.full[ring.slot], (uint32_t)nt * 2048);
                 db_bulk_g2s(sm.ring + (size_t)ring.slot * DB_SLOT, kf + (long)t0 * 1024, (uint32_t)nt * 2048, &sm.full[ring.slot]);
                 ring.advance();
-                db_wait(&sm.empty[ring.slot], ring.phase ^ 1);
+                db_wait<true>(&sm.empty[ring.slot], ring.phase ^ 1, 31);
                 mbar_expect_tx(&sm.full[ring.slot], (uint32_t)nkc * 4096);
 #pragma unroll 1
                 for (int dt = 0; dt < 4; ++dt)
@@ -855,7 +923,7 @@ __device__ __forceinline__ void db_producer(const DbArgs& a, uint8_t* raw) {
         int u0, u1;
         db_range(sd.n_tiles, sd.vcta, nctas, u0, u1);
         if (sd.ln_g && u1 > u0) {
-            db_wait(&sm.empty[ring.slot], ring.phase ^ 1);
+            db_wait<true>(&sm.empty[ring.slot], ring.phase ^ 1, 32);
             mbar_expect_tx(&sm.full[ring.slot], (uint32_t)d * 8);
             db_bulk_g2s(sm.ring + (size_t)ring.slot * DB_SLOT, sd.ln_g, (uint32_t)d * 4, &sm.full[ring.slot]);
             db_bulk_g2s(sm.ring + (size_t)ring.slot * DB_SLOT + (size_t)d * 4, sd.ln_b, (uint32_t)d * 4, &sm.full[ring.slot]);
@@ -868,7 +936,7 @@ __device__ __forceinline__ void db_producer(const DbArgs& a, uint8_t* raw) {
             for (int c0 = 0, nblk = 0; c0 < sd.n_kc; c0 += nblk) {
                 nblk = chunk_kc < sd.n_kc ? db_slot_blocks(c0, sd.n_kc, chunk_kc) : min(DB_SLOT_BLOCKS, sd.n_kc - c0);
                 const uint32_t bytes = (uint32_t)nblk * 1024;
-                db_wait(&sm.empty[ring.slot], ring.phase ^ 1);
+                db_wait<true>(&sm.empty[ring.slot], ring.phase ^ 1, 33);
                 mbar_expect_tx(&sm.full[ring.slot], bytes);
                 db_bulk_g2s(sm.ring + (size_t)ring.slot * DB_SLOT, sd.w + ((long)t * sd.n_kc + c0) * 512, bytes, &sm.full[ring.slot]);
                 ring.advance();
@@ -892,6 +960,7 @@ __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsig
     for (int it = 0; it < n_stages; ++it) {
         const int l = it >> 3, st = it == M.Ld * 8 ? DBS_VOCAB : (it & 7);
         const uint32_t ep = seq * 64u + (uint32_t)l + 1u, ep_prev = ep - 1u;      // ep_prev: x3 of the layer below
+        if (tid == 0) db_progress(a.lane_id, 0, it);
         if (st == DBS_QKV && l < M.Ld) {
             // Hide DRAM latency: the layer's bias vectors (read by every tile's epilogue) and the cached K / V rows of the
             // self-attention units this CTA will run two stages from now were last touched a step (360 MB of traffic) ago, so
@@ -997,13 +1066,27 @@ __global__ void __launch_bounds__(DbCfg<NT, CW>::THREADS, 1) decoder_batch_kerne
     const int tid = (int)threadIdx.x - C::PW * 32;
     // a window that has finished keeps stepping (its rows are ignored) at its last position, never past the cache
     if (tid < a.W) db_smem<NT, CW>(a, db_raw).spos[tid] = min(a.st ? a.st[tid].pos : a.text_offset, N_TEXT_CTX - 1);
+    if (tid >= 32 && tid < 32 + DB_MAX_SLOTS) db_smem<NT, CW>(a, db_raw).seen[tid - 32] = -1;
     const unsigned seq = a.barrier[2];                 // written by the previous launch
     __syncthreads();
     db_consumer<NT, CW, DBG>(a, db_raw, seq, tid >> 5, tid & 31);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------
-void db_set_model(const DbModel& m) { B200_CHECK(cudaMemcpyToSymbol(c_db, &m, sizeof(DbModel))); }
+static unsigned long long* g_h_fault = nullptr;
+void db_set_model(const DbModel& m) {
+    B200_CHECK(cudaMemcpyToSymbol(c_db, &m, sizeof(DbModel)));
+    if (!g_h_fault && cudaHostAlloc((void**)&g_h_fault, 16 + DB_PROGRESS_WORDS * 4, cudaHostAllocMapped) == cudaSuccess) {
+        memset(g_h_fault, 0, 16 + DB_PROGRESS_WORDS * 4);
+        unsigned long long* dp = nullptr;
+        if (cudaHostGetDevicePointer((void**)&dp, g_h_fault, 0) == cudaSuccess) B200_CHECK(cudaMemcpyToSymbol(g_db_fault, &dp, sizeof(dp)));
+    }
+}
+// {where, grid, CTA, thread} of the bounded wait that trapped (0 = none): decoder_batch.cu's `where` codes are 2..13 for LL polls,
+// 20..25 for consumer waits on a ring slot, 30..33 for the producer's waits on a free slot
+unsigned long long db_fault_word() { return g_h_fault ? *(volatile unsigned long long*)g_h_fault : 0ull; }
+// progress table saved with the fault word: [decode lane][DB_PROGRESS_LD] of (consumer stage + 1) | (producer stage + 1) << 16
+const unsigned* db_fault_progress() { return g_h_fault ? reinterpret_cast<const unsigned*>(g_h_fault + 2) : nullptr; }
 
 int db_consumer_warps() {
     return 8;

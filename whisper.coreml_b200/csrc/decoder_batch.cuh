@@ -11,6 +11,7 @@ constexpr int DB_MAX_LAYERS = 32;
 constexpr int DB_MAX_WINDOWS = 8;        // windows per batched step (each with its own cross K/V, KV cache rows and decode state)
 constexpr int DB_MAX_ROWS = 40;          // rows = windows x beams per step: 5 n-tiles of mma.m16n8k16
 constexpr int DB_DBG_LD = 640;           // timeline marks per CTA (2 per stage + 1)
+constexpr int DB_PROGRESS_LD = 160, DB_PROGRESS_WORDS = 8 * DB_PROGRESS_LD;    // progress words: [decode lane][CTA]
 constexpr int DB_N_SPLITS = 7;           // key splits of a cross-attention head (224 keys each)
 
 struct DbLayer {
@@ -28,6 +29,7 @@ struct DbModel {                         // copied into constant memory when bot
 // all index w * slot_stride + b (slot_stride = beams of the decode; the prompt runs with nbw = 1 into the first slot of each window).
 struct DbArgs {
     int W, nbw, slot_stride;
+    int lane_id;                         // decode lane of the launch (row of the progress table, 0 .. 7)
     int win[DB_MAX_WINDOWS];             // cross K/V window (index into ckv_frag) of each batch window
     const bf16* ckv_frag; long ckv_window_elems;
     // shared-memory geometry (db_geometry): bf16 activation rows [xs_rows][xs_cols + 32], scratch, then the ring of n_slots 40 KB slots
@@ -60,5 +62,7 @@ bool db_geometry(int d, int rows, int smem_optin, DbGeometry* g);
 size_t db_ll_words(size_t d, size_t H);
 void db_carve_ll(DbArgs& a, uint2* base, size_t d, size_t H);
 bool db_launch(const DbArgs& a, int n_ctas, cudaStream_t s);
+const unsigned* db_fault_progress();
+unsigned long long db_fault_word();                     // what the kernel left before a timeout trap (0 = nothing)
 
 }  // namespace b200
