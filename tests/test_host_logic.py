@@ -48,9 +48,10 @@ def test_segment_slicing_and_seek_rule_match_oracle(seed):
         got = _segments_from_tokens(toks, r, seek * 0.01, size * 0.01, seek, tb, keep_tail=False)
         assert [(round(s["start"], 6), round(s["end"], 6), s["tokens"]) for s in got] == [(round(a, 6), round(b, 6), tk) for a, b, tk in want_segs]
         assert _next_seek(toks, seek, size, tb) == want_seek
-        # fixed windows keep what the reference would decode again: the segments cover every token exactly once
+        # fixed windows keep what the reference would decode again: the segments cover every text token exactly once
         kept = _segments_from_tokens(toks, r, seek * 0.01, size * 0.01, seek, tb, keep_tail=True)
-        assert [t for s in kept for t in s["tokens"]] == toks
+        flat = [t for s in kept for t in s["tokens"]]
+        assert flat == toks[:len(flat)] and all(x >= tb for x in toks[len(flat):])     # (only a lone opening timestamp may be left over)
 
 
 def test_window_records_survive_the_exchange():

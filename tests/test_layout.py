@@ -99,9 +99,16 @@ def test_segment_slicing_follows_timestamp_pairs():
     from whisper_b200.transcribe import _segments_from_tokens
     tb, eot = 50364, 50257
     toks = [tb, 11, 12, tb + 100, tb + 100, 13, tb + 250, tb + 250]
-    segs = _segments_from_tokens(toks, DecodingResult(tokens=toks), 30.0, 30.0, 3000, tb, eot)
-    assert [(round(s["start"], 2), round(s["end"], 2)) for s in segs] == [(30.0, 32.0), (32.0, 35.0)]
-    segs = _segments_from_tokens([11, 12, tb + 50], DecodingResult(), 0.0, 30.0, 0, tb, eot)
+    for keep_tail in (False, True):                                                  # (the tail here is a lone opening timestamp: no segment)
+        segs = _segments_from_tokens(toks, DecodingResult(tokens=toks), 30.0, 30.0, 3000, tb, keep_tail)
+        assert [(round(s["start"], 2), round(s["end"], 2)) for s in segs] == [(30.0, 32.0), (32.0, 35.0)]
+    # fixed windows keep the text after the last pair (the reference would re-decode it from the next seek)
+    toks2 = toks + [14, 15]
+    segs = _segments_from_tokens(toks2, DecodingResult(tokens=toks2), 30.0, 30.0, 3000, tb, True)
+    assert [(round(s["start"], 2), round(s["end"], 2)) for s in segs] == [(30.0, 32.0), (32.0, 35.0), (35.0, 60.0)]
+    assert segs[-1]["tokens"] == [tb + 250, 14, 15]
+    assert len(_segments_from_tokens(toks2, DecodingResult(tokens=toks2), 30.0, 30.0, 3000, tb, False)) == 2
+    segs = _segments_from_tokens([11, 12, tb + 50], DecodingResult(), 0.0, 30.0, 0, tb, True)
     assert len(segs) == 1 and segs[0]["end"] == 1.0
 
 

@@ -65,7 +65,7 @@ def _segments_from_tokens(tokens: List[int], result: DecodingResult, time_offset
             segs.append(new_segment(time_offset + (sl[0] - timestamp_begin) * TIME_PRECISION,
                                     time_offset + (sl[-1] - timestamp_begin) * TIME_PRECISION, sl))
             last = cur
-        if keep_tail and not single_timestamp_ending and last < len(t):
+        if keep_tail and not single_timestamp_ending and last < len(t) and not is_ts[last:].all():     # (a lone opening timestamp is no segment)
             tail = t[last:]
             start = time_offset + (tail[0] - timestamp_begin) * TIME_PRECISION if is_ts[last] else segs[-1]["end"]
             segs.append(new_segment(start, time_offset + segment_duration, tail))
