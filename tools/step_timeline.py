@@ -26,6 +26,9 @@ LD = 640
 buf = np.zeros(256 * LD, dtype=np.uint64)
 n = m.lib.b200TestStepTimeline(0, buf.ctypes.data_as(ctypes.c_void_p), 256)
 T = buf[:n * LD].astype(np.int64).reshape(n, LD)
+SP = T[200:].reshape(-1, 8)             # marks of the separate sampling kernel: [CTA][entry, partial done, ticket, updated]
+SP = SP[SP[:, 0] > 0]
+T = T[:200]
 T = T[T[:, 0] > 0]                      # CTAs that ran
 n = T.shape[0]
 STAGES = ["qkv", "self_attn", "out_proj", "cross_q", "cross_attn", "cross_out", "mlp1", "mlp2"]
@@ -43,6 +46,10 @@ for it in range(n_stages):
     kind = STAGES[it % 8] if it < n_stages - 1 else "vocab"
     per_kind.setdefault(kind, []).append((done.max() - prev_done.max()) / 1000.0)
     prev_done = done
+if len(SP):
+    f = lambda a: (a - t0) / 1000.0
+    print(f"sampling kernel ({len(SP)} CTAs): entry first {f(SP[:, 0].min()):.2f} last {f(SP[:, 0].max()):.2f} | partial done first {f(SP[:, 1].min()):.2f} last {f(SP[:, 1].max()):.2f}"
+          f" | ticket last {f(SP[:, 2].max()):.2f} | updated {f(SP[:, 3].max()):.2f}")
 print("step total", (T[:, :2 * n_stages + 1].max() - t0) / 1000.0, "us")
 print("mean us per stage kind (last done -> last done):", {k: round(float(np.mean(v)), 2) for k, v in per_kind.items()})
 

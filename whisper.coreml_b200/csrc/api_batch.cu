@@ -250,12 +250,18 @@ static void launch_batch_sampling(const BatchJob& j, bool shared_logits) {
     b.row_stride_w = shared_logits ? 1 : j.nb; b.row_stride_b = shared_logits ? 0 : 1;
     b.tokens = c.tokens; b.table = c.table; b.fin_tokens = c.fin_tokens; b.st = c.st; b.part = c.part; b.cand_lp = c.cand_lp; b.cand_tok = c.cand_tok;
     b.spec = decode_spec(); b.W = j.W; b.nb = j.nb; b.k = j.k; b.slot_stride = j.nb; b.n_text_ctx = N_TEXT_CTX;
+    b.dbg = g_dbg ? g_dbg + 200 * DB_DBG_LD : nullptr;      // (rows 200.. of the timeline buffer: no launch has that many CTAs)
     sample_and_update_batch(b, c.stream);
 }
 
+__global__ void __launch_bounds__(256) batch_noop_kernel() {}
 static void one_batch_step(const BatchJob& j) {
     const DbArgs a = step_args(j, false, 0);
     db_launch(a, j.n_ctas, g_lane[j.lane].stream);
+    // timing experiments only (the decode is then meaningless): 1 = no sampling kernel, 2 = an empty kernel of the same grid
+    static const int experiment = getenv("B200_SAMPLING_EXPERIMENT") ? atoi(getenv("B200_SAMPLING_EXPERIMENT")) : 0;
+    if (experiment == 1) return;
+    if (experiment == 2) { batch_noop_kernel<<<dim3(SAMPLE_CHUNKS, j.nb, j.W), 256, 0, g_lane[j.lane].stream>>>(); return; }
     launch_batch_sampling(j, false);
 }
 
@@ -459,7 +465,7 @@ int decode_windows_batch(const int* windows, int n_windows, const int* initial_t
 // stage timeline of the batched kernel (tools/step_timeline.py): enable allocates + clears the buffer, disable copies it out
 int batch_timeline(int enable, unsigned long long* out, int cap_ctas) {
     State& s = S();
-    const size_t n = (size_t)s.n_sms * DB_DBG_LD;
+    const size_t n = (size_t)256 * DB_DBG_LD;                        // rows 0 .. n_sms - 1: step-kernel CTAs; rows 200 ..: sampling-kernel marks
     if (enable) {
         if (!g_dbg && !dev_alloc(&g_dbg, n)) return 0;
         B200_CHECK(cudaMemset(g_dbg, 0, n * sizeof(unsigned long long)));
@@ -467,7 +473,7 @@ int batch_timeline(int enable, unsigned long long* out, int cap_ctas) {
     }
     if (!g_dbg) return 0;
     B200_CHECK(cudaDeviceSynchronize());
-    const int n_ctas = std::min(cap_ctas, s.n_sms);
+    const int n_ctas = std::min(cap_ctas, 256);
     B200_CHECK(cudaMemcpy(out, g_dbg, (size_t)n_ctas * DB_DBG_LD * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     dev_free(&g_dbg);
     return n_ctas;

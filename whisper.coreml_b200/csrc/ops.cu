@@ -4,10 +4,11 @@
 namespace b200 {
 
 // ---------------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, row kept in registers (d <= 1536, d % 128 == 0), two-pass variance.
+// LayerNorm: one warp per row, row kept in registers (d <= 1536, d % 128 == 0), two-pass variance.  At most 85 registers
+// per thread: three CTAs per SM, so the 375 CTAs of two windows (3000 rows) are ONE wave (at 88 registers they were 1.27 waves of 296).
 // ---------------------------------------------------------------------------------------------------
 template <int VPL>   // float4 per lane
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, 3) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, bf16* __restrict__ yb,
                                                         float* __restrict__ yf, int M, int d) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

@@ -32,11 +32,15 @@ __global__ void __launch_bounds__(256) sample_update_batch_kernel(const SampleBa
     __shared__ int stage[DEC_MAX_BEAMS * DEC_TOK_LD];
     __shared__ int s_last;
     const int w = blockIdx.z;
+    unsigned long long* dbg = b.dbg && !b.st[w].done ? b.dbg + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;   // (replays past the end leave no marks)
+    auto mark = [&](int i) { if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[i] = t; } };
+    mark(0);
     SampleArgs a;
     a.logits = b.logits + (long)w * b.row_stride_w * b.ld_logits; a.ld_logits = (long)b.row_stride_b * b.ld_logits;
     a.tokens = b.tokens + (long)w * b.slot_stride * DEC_TOK_LD; a.st = b.st + w; a.spec = b.spec; a.nb = b.nb; a.k = b.k;
     a.part = b.part + w; a.cand_lp = b.cand_lp + w * DEC_MAX_BEAMS * SAMPLE_MAX_K; a.cand_tok = b.cand_tok + w * DEC_MAX_BEAMS * SAMPLE_MAX_K;
     sample_partial_body<256>(a, blockIdx.x, blockIdx.y, threadIdx.x, BlockSync());
+    mark(1);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -44,6 +48,7 @@ __global__ void __launch_bounds__(256) sample_update_batch_kernel(const SampleBa
         s_last = atomicAdd(&a.part->arrivals, 1u) == n - 1;
     }
     __syncthreads();
+    mark(2);
     if (!s_last) return;
     __threadfence();
     if (threadIdx.x == 0) a.part->arrivals = 0;
@@ -52,6 +57,7 @@ __global__ void __launch_bounds__(256) sample_update_batch_kernel(const SampleBa
     u.tokens = b.tokens + (long)w * b.slot_stride * DEC_TOK_LD; u.table = b.table + (long)w * b.slot_stride * 448;
     u.fin_tokens = b.fin_tokens + (long)w * DEC_MAX_BEAMS * DEC_TOK_LD; u.st = b.st + w; u.eot = b.spec.eot; u.n_text_ctx = b.n_text_ctx;
     beam_update_body<256, false>(u, stage, nullptr, threadIdx.x, BlockSync());
+    mark(3);
 }
 
 void sample_and_update_batch(const SampleBatchArgs& a, cudaStream_t s) {

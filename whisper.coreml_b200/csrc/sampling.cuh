@@ -75,6 +75,7 @@ struct SampleBatchArgs {
     float* cand_lp; int* cand_tok;                 // [W][DEC_MAX_BEAMS * SAMPLE_MAX_K]
     DecodeSpec spec;
     int W, nb, k, slot_stride, n_text_ctx;
+    unsigned long long* dbg;                       // optional %globaltimer marks [CTA][8] (tools/step_timeline.py)
 };
 void sample_and_update_batch(const SampleBatchArgs& a, cudaStream_t s);
 // st[w].no_speech_prob for W windows from logits rows w
