@@ -105,3 +105,20 @@ def test_errors_are_reported(setup):
     lib.decoder256Predict(_f32p(x), _f32p(torch.zeros(256, 256)), _f32p(x.clone()), None, 99)
     with pytest.raises(RuntimeError):
         _lib.check_errors("bad beam index")
+
+
+def test_abi_smoke_driver_runs():
+    """csrc/abi_smoke.cpp (the analogue of coreml/coremlTest.cpp): a plain C++ program linked against libwhisper_b200.so drives the
+    13 reference entry points twice (load / predict / close) on exported tiny weights and exits 0 with finite outputs."""
+    import os
+    import subprocess
+    from tests._util import close_library
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(here, "whisper.coreml_b200", "build", "abi_smoke")
+    assert os.path.exists(exe), "build/abi_smoke missing: run __graft_entry__.build()"
+    dims, ckpt, folder = exported("tiny")
+    close_library()
+    r = subprocess.run([exe, folder, str(dims.n_audio_layer), str(dims.n_text_layer), str(dims.n_audio_state), str(dims.n_mels),
+                        str(dims.n_vocab), "5", str(len(om.default_alignment_heads(dims)))],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "abi_smoke: ok" in r.stdout, (r.returncode, r.stdout[-800:], r.stderr[-800:])

@@ -1,13 +1,12 @@
-"""Regenerate profiles/r1_sass_summary.csv (per-kernel instruction mix of libwhisper_b200.so) and the full SASS listings of the
+"""Regenerate profiles/<round>_sass_summary.csv (per-kernel instruction mix of libwhisper_b200.so) and the full SASS listings of the
 hot kernels under profiles/sass/.  Needs only cuobjdump (no GPU):  python tools/dump_sass.py [round-prefix, default r1]"""
 import os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "whisper.coreml_b200", "libwhisper_b200.so")
 PREFIX = sys.argv[1] if len(sys.argv) > 1 else "r1"
-HOT = ("flash_attn_tc_kernel", "decoder_mega_kernel", "gemm_tcgen05", "layernorm_kernel<10>", "mel_frames_kernel", "sample_update_kernel",
-       "sample_partial_kernel", "beam_update_kernel", "median_kernel", "dtw_kernel", "attention_simt_kernel", "step_gemv_kernel",
-       "step_self_attn_kernel", "step_cross_attn_kernel")
+HOT = ("flash_attn_tc_kernel", "decoder_batch_kernel<1", "decoder_batch_kernel<5", "gemm_tcgen05", "layernorm_kernel<10>", "mel_frames_kernel",
+       "sample_update_batch_kernel", "median_kernel", "dtw_kernel", "align_kernel", "attention_simt_kernel", "attention_qk_dump_kernel")
 COLS = [("UTCHMMA(tcgen05.mma)", r"\bUTC[A-Z]*MMA"), ("LDTM/STTM(tcgen05.ld/st)", r"\b(LDTM|STTM)"), ("UTMALDG/UTMASTG(TMA tensor)", r"\bUTMA(LDG|STG)"),
         ("UBLKCP(cp.async.bulk)", r"\bUBLKCP"), ("HMMA(mma.sync)", r"\bHMMA"), ("LDGSTS(cp.async)", r"\bLDGSTS"), ("SYNCS(mbarrier)", r"\bSYNCS"),
         ("STL+LDL(local)", r"\b(STL|LDL)\b")]
