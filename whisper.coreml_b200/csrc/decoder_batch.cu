@@ -42,6 +42,7 @@
 #include "decoder_batch.cuh"
 
 #include <stdlib.h>
+#include <algorithm>
 #include <string.h>
 
 namespace b200 {
@@ -304,6 +305,7 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, co
     db_range(g.n_tiles, g.vcta, nctas, u0, u1);
     for (int t = u0; t < u1; ++t) {
         const bool mine = chunked ? group == 0 : ((t - u0) & 1) == group;          // (uniform within a group)
+        if (t - u0 == 2) dbg.smark(27);                                            // (probe: top of the group's second tile)
         float add[C::PASSES];
         // seen[] of the tile's first slot, read early (its latency hides behind the residual fetch; the value only grows)
         int sv = mine ? sm.seen[ring.slot] : 0;
@@ -388,7 +390,7 @@ __device__ __forceinline__ void db_stage_gemv(const DbSmem& sm, DbRing& ring, co
             // slots would, because the producer refills them as soon as their owner is done.)
             ring.advance();                                             // both groups track every slot of the CTA
         }
-        if (!mine) continue;
+        if (!mine) { dbg.smark(21 + 4 * (t - u0)); continue; }
         dbg.smark(21 + 4 * (t - u0));
         float* red = sm.red + group * (C::GW * NT * 128);
 #pragma unroll
@@ -702,23 +704,36 @@ __device__ __forceinline__ void db_stage_self_attn(const DbSmem& sm, const DbArg
     }
 }
 
-// ---- cross-attention, unit = (window, head, key split): K/V of a head are read once for all beams of the window; the CTA of a
-// head's last (shortest) split then merges the head's partials in split order --------------------------------------------
+// ---- cross-attention, unit = (window, head, key split): K/V of a head are read once for all beams of the window; the group of
+// a head's last (shortest) split then merges the head's partials in split order.  The CTA's units alternate between the two
+// tile groups, which work CONCURRENTLY, each with its own scratch: a unit is a chain of four barriers (q staged -> scores ->
+// softmax -> P V), so with two or more units per CTA (any launch with fewer CTAs than units: decode lanes) one unit at a time
+// left the SM mostly waiting.  Group g keeps q / p of its unit in activation rows 0 .. nbw - 1 at columns DB_CA_COLS * g and
+// its scores in sm.sp (g = 0) or behind them in the same rows (g = 1, columns DB_CA_SP1 ..; db_geometry keeps rows that long).
+constexpr int DB_CA_COLS = 512, DB_CA_SP1 = 736, DB_CA_MIN_COLS = DB_CA_SP1 + 2 * DB_SPLIT_KEYS;
 template <int NT, int CW>
 __device__ __forceinline__ void db_stage_cross_attn(const DbSmem& sm, DbRing& ring, const DbArgs& a, uint32_t ep, int cta, int nctas, int rot,
                                                     int warp, int lane) {
     using C = DbCfg<NT, CW>;
     const DbModel& M = c_db;
-    const int d = M.d, H = M.H, tid = warp * 32 + lane, gq = lane >> 2, tq = lane & 3, nbw = a.nbw;
+    const int d = M.d, H = M.H, gq = lane >> 2, tq = lane & 3, nbw = a.nbw;
+    const int group = warp >> 2, gw = warp & 3, gtid = gw * 32 + lane;
     constexpr int n_ktiles = CROSS_KEYS_PAD / 16, n_vkc = CROSS_KEYS_PAD / 32;
-    for (int u = (cta + rot) % nctas; u < a.W * H * DB_N_SPLITS; u += nctas) {
+    bf16* xg = sm.xs + group * DB_CA_COLS;                                       // q (64 columns), then p (224) of the group's unit
+    float* spg = group == 0 ? sm.sp : reinterpret_cast<float*>(sm.xs + DB_CA_SP1);      // scores [beam][224]
+    const int sp_ld = group == 0 ? DB_SPLIT_KEYS : sm.ldx / 2;                   // (floats)
+    float* statg = sm.stat + 32 + group * 16;                                    // [0 .. 7] max, [8 .. 15] sum per beam
+    csync<C::CONS>();                                                            // the previous stage's tiles are done with the activation rows
+    int j = 0;
+    for (int u = (cta + rot) % nctas; u < a.W * H * DB_N_SPLITS; u += nctas, ++j) {
+        if ((j & 1) != group) { ring.advance(); ring.advance(); continue; }      // the other group's unit: its K and V slots
         const int wh = u / DB_N_SPLITS, s = u - wh * DB_N_SPLITS, w = wh / H, h = wh - w * H;
         const int t0 = s * DB_SPLIT_TILES, nt = min(DB_SPLIT_TILES, n_ktiles - t0);
         const int nkeys = min(nt * 16, N_AUDIO_CTX - t0 * 16);                  // valid (unpadded) keys of the split
-        csync<C::CONS>();
-        // q of this (window, head) -> xs rows 0 .. nbw - 1 (bf16, 64 columns): 16-byte items of 2 fp32 words
+        gsync<C::GT>(group);                                                     // the group's previous unit is done with its scratch
+        // q of this (window, head) -> rows 0 .. nbw - 1 (bf16, 64 columns): 16-byte items of 2 fp32 words
 #pragma unroll 1
-        for (int i = tid; i < nbw * 32; i += C::CONS) {
+        for (int i = gtid; i < nbw * 32; i += C::GT) {
             const uint2* p = a.ll_q + (long)(w * nbw + (i >> 5)) * d + h * 64 + (i & 31) * 2;
             u64 q0, q1;
             unsigned spins = 0;
@@ -727,64 +742,65 @@ __device__ __forceinline__ void db_stage_cross_attn(const DbSmem& sm, DbRing& ri
                 if (ll_good(q0, ep) && ll_good(q1, ep)) break;
                 ll_pause(spins, 5);
             }
-            reinterpret_cast<uint32_t*>(sm.xs + (long)(i >> 5) * sm.ldx)[i & 31] = pack_bf16(__uint_as_float((uint32_t)q0), __uint_as_float((uint32_t)q1));
+            reinterpret_cast<uint32_t*>(xg + (long)(i >> 5) * sm.ldx)[i & 31] = pack_bf16(__uint_as_float((uint32_t)q0), __uint_as_float((uint32_t)q1));
         }
-        csync<C::CONS>();
-        // scores: one slot carries the split's key tiles (2 blocks each); warp w takes tiles w, w + CW, ...
+        gsync<C::GT>(group);
+        // scores: one slot carries the split's key tiles (2 blocks each); warp gw of the group takes tiles gw, gw + 4, ...
+        db_seen_wait(sm, ring);
         db_wait(&sm.full[ring.slot], ring.phase, 24);
-        if (tid == 0) sm.seen[ring.slot] = ring.use;
+        if (gtid == 0) sm.seen[ring.slot] = ring.use;
         {
             const uint4* sl = reinterpret_cast<const uint4*>(sm.ring + (size_t)ring.slot * DB_SLOT) + lane;
-            const uint4 xb0 = *reinterpret_cast<const uint4*>(sm.xs + (long)gq * sm.ldx + tq * 8);
-            const uint4 xb1 = *reinterpret_cast<const uint4*>(sm.xs + (long)gq * sm.ldx + 32 + tq * 8);
+            const uint4 xb0 = *reinterpret_cast<const uint4*>(xg + (long)gq * sm.ldx + tq * 8);
+            const uint4 xb1 = *reinterpret_cast<const uint4*>(xg + (long)gq * sm.ldx + 32 + tq * 8);
 #pragma unroll
-            for (int q = 0; q < (DB_SPLIT_TILES + CW - 1) / CW; ++q) {
-                const int tt = warp + CW * q;
+            for (int q = 0; q < (DB_SPLIT_TILES + C::GW - 1) / C::GW; ++q) {
+                const int tt = gw + C::GW * q;
                 if (tt < nt) {
                     float acc[4] = {0.f, 0.f, 0.f, 0.f};
                     db_mma(acc, sl[tt * 128], sl[tt * 128 + 32], xb0);
                     db_mma(acc, sl[tt * 128 + 64], sl[tt * 128 + 96], xb1);
-                    float* spb = sm.sp + tt * 16;
-                    spb[(2 * tq) * DB_SPLIT_KEYS + gq] = acc[0]; spb[(2 * tq + 1) * DB_SPLIT_KEYS + gq] = acc[1];
-                    spb[(2 * tq) * DB_SPLIT_KEYS + gq + 8] = acc[2]; spb[(2 * tq + 1) * DB_SPLIT_KEYS + gq + 8] = acc[3];
+                    float* spb = spg + tt * 16;                                  // (beams >= nbw are rows that do not exist)
+                    if (2 * tq < nbw) { spb[(2 * tq) * sp_ld + gq] = acc[0]; spb[(2 * tq) * sp_ld + gq + 8] = acc[2]; }
+                    if (2 * tq + 1 < nbw) { spb[(2 * tq + 1) * sp_ld + gq] = acc[1]; spb[(2 * tq + 1) * sp_ld + gq + 8] = acc[3]; }
                 }
             }
         }
-        csync<C::CONS>();                                                  // every warp has read its key tiles
-        if (warp < C::ARRIVALS && lane == 0) mbar_arrive(&sm.empty[ring.slot]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[ring.slot]);                       // every warp of the group releases what it has read
         ring.advance();
+        gsync<C::GT>(group);                                                     // every score is written
         // partial softmax per beam over the split's valid keys; p (bf16) becomes the B operand of P V
-        for (int b = warp; b < nbw; b += CW) {
+        for (int b = gw; b < nbw; b += C::GW) {
             float sv[DB_SPLIT_KEYS / 32];
             float m = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < DB_SPLIT_KEYS / 32; ++i) { const int j = lane + 32 * i; sv[i] = j < nkeys ? sm.sp[b * DB_SPLIT_KEYS + j] : -INFINITY; m = fmaxf(m, sv[i]); }
+            for (int i = 0; i < DB_SPLIT_KEYS / 32; ++i) { const int jj = lane + 32 * i; sv[i] = jj < nkeys ? spg[b * sp_ld + jj] : -INFINITY; m = fmaxf(m, sv[i]); }
             m = warp_max(m);
             float lsum = 0.f;
 #pragma unroll
             for (int i = 0; i < DB_SPLIT_KEYS / 32; ++i) {
                 const float p = __expf(sv[i] - m);                              // exp(-inf) = 0 for the padded keys
                 lsum += p;
-                sm.xs[(long)b * sm.ldx + lane + 32 * i] = __float2bfloat16(p);
+                xg[(long)b * sm.ldx + lane + 32 * i] = __float2bfloat16(p);
             }
             lsum = warp_sum(lsum);
-            if (lane == 0) { sm.stat[32 + b] = m; sm.stat[40 + b] = lsum; }
+            if (lane == 0) { statg[b] = m; statg[8 + b] = lsum; }
         }
-        csync<C::CONS>();
+        gsync<C::GT>(group);
         // o[dim][beam] = V^T[dim][key] p[key][beam]: the slot holds the split's key blocks of the four dim tiles; warp dt owns tile dt
         const int nkc = min(DB_SPLIT_TILES / 2, n_vkc - s * (DB_SPLIT_TILES / 2));
         uint2* part = a.ll_cap + (((long)(w * H + h) * DB_N_SPLITS + s) * 8) * 66;
-        if (warp < 4) {
-            // only the warps that read the slot (and release it) wait for it: a warp that waited without releasing could come
-            // late, after the slot has been released AND refilled, and would then wait for a parity that has come round again
-            db_wait(&sm.full[ring.slot], ring.phase, 25);
-            if (tid == 0) sm.seen[ring.slot] = ring.use;
-            const uint4* sl = reinterpret_cast<const uint4*>(sm.ring + (size_t)ring.slot * DB_SLOT + (size_t)warp * nkc * 1024) + lane;
+        db_seen_wait(sm, ring);
+        db_wait(&sm.full[ring.slot], ring.phase, 25);
+        if (gtid == 0) sm.seen[ring.slot] = ring.use;
+        {
+            const uint4* sl = reinterpret_cast<const uint4*>(sm.ring + (size_t)ring.slot * DB_SLOT + (size_t)gw * nkc * 1024) + lane;
             float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
             for (int kc = 0; kc < DB_SPLIT_TILES / 2; ++kc)
-                if (kc < nkc) db_mma(acc[kc & 1], sl[kc * 64], sl[kc * 64 + 32], *reinterpret_cast<const uint4*>(sm.xs + (long)gq * sm.ldx + kc * 32 + tq * 8));
-            const int b0 = 2 * tq, dim = warp * 16 + gq;
+                if (kc < nkc) db_mma(acc[kc & 1], sl[kc * 64], sl[kc * 64 + 32], *reinterpret_cast<const uint4*>(xg + (long)gq * sm.ldx + kc * 32 + tq * 8));
+            const int b0 = 2 * tq, dim = gw * 16 + gq;
             if (b0 < nbw) {
                 ll_st(part + b0 * 66 + 2 + dim, __float_as_uint(acc[0][0] + acc[1][0]), ep);
                 ll_st(part + b0 * 66 + 2 + dim + 8, __float_as_uint(acc[0][2] + acc[1][2]), ep);
@@ -795,13 +811,13 @@ __device__ __forceinline__ void db_stage_cross_attn(const DbSmem& sm, DbRing& ri
             }
         }
         __syncwarp();
-        if (warp < C::ARRIVALS && lane == 0) mbar_arrive(&sm.empty[ring.slot]);     // (warps 0 - 3 are the ones that read the V^T tiles)
+        if (lane == 0) mbar_arrive(&sm.empty[ring.slot]);
         ring.advance();
-        if (tid < nbw) { ll_st(part + tid * 66, __float_as_uint(sm.stat[32 + tid]), ep); ll_st(part + tid * 66 + 1, __float_as_uint(sm.stat[40 + tid]), ep); }
+        if (gtid < nbw) { ll_st(part + gtid * 66, __float_as_uint(statg[gtid]), ep); ll_st(part + gtid * 66 + 1, __float_as_uint(statg[8 + gtid]), ep); }
         if (s == DB_N_SPLITS - 1) {
             const uint2* ph = a.ll_cap + ((long)(w * H + h) * DB_N_SPLITS * 8) * 66;
 #pragma unroll 1
-            for (int e = tid; e < nbw * 64; e += C::CONS) {
+            for (int e = gtid; e < nbw * 64; e += C::GT) {
                 const int b = e >> 6, c = e & 63;
                 u64 rm[DB_N_SPLITS], rl[DB_N_SPLITS], ro[DB_N_SPLITS];         // all loads of a round are in flight together
                 unsigned spins = 0;
@@ -1103,7 +1119,7 @@ bool db_geometry(int d, int rows, int smem_optin, DbGeometry* g) {
     // prefer >= 3 ring slots with the largest K chunk; with many rows fall back to 2 slots
     for (int min_slots = 3; min_slots >= 2; --min_slots)
         for (int div = 1; div <= 4; div *= 2) {        // K chunk = 4d, 2d, d columns
-            const int xs_cols = 4 * d / div;
+            const int xs_cols = std::max(4 * d / div, DB_CA_MIN_COLS - DB_XS_PAD);      // (cross-attention: the second group's scratch, DB_CA_MIN_COLS)
             const size_t front = ((size_t)xs_rows * (xs_cols + DB_XS_PAD) * 2 + db_scratch_bytes(nt, cw) + 127) / 128 * 128;
             int slots = (int)(((size_t)smem_optin - (front < (size_t)smem_optin ? front : (size_t)smem_optin)) / DB_SLOT);
             if (slots > DB_MAX_SLOTS) slots = DB_MAX_SLOTS;
