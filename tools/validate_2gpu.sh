@@ -1,5 +1,5 @@
 #!/bin/bash
-# N = 2: default bench (weak scaling) and the configs[4] file (strong scaling), both arms' JSON lines kept
+# N = 2 under `gpurun --gpus 2`: default bench (weak scaling) and the configs[4] file (strong scaling); outputs in gpurun_out/r2x_*
 cd /root/repo; mkdir -p gpurun_out
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 timeout 900 $T --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r2x_bench_n2.json 2> gpurun_out/r2x_bench_n2.err

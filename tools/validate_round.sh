@@ -1,5 +1,5 @@
 #!/bin/bash
-# full GPU suite + smoke + default bench + the configs[4] bench lines
+# round validation under gpurun: full GPU suite + smoke + default bench + the configs[4] lines + the reference arm (outputs in gpurun_out/r2s_*)
 cd /root/repo; mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 > gpurun_out/r2s_tests.txt
 timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r2s_smoke.txt 2>&1
