@@ -59,17 +59,35 @@ static void report_step_fault(unsigned long long f) {
     reported = true;
     record_error("decoder_batch_kernel gave up in wait %d: CTA %d of %d, thread %d", (int)(f >> 48 & 0x7fff), (int)(f >> 16 & 0xffff),
                  (int)(f >> 32 & 0xffff), (int)(f & 0xffff));
+    if (const unsigned long long* x = db_fault_ll_word()) {
+        // the long LL-word waits, one line per (CTA, where) with the lowest word waited for
+        std::map<std::vector<long>, std::vector<unsigned long long>> rows;
+        for (unsigned long long i = 0; i < x[0] && i < (unsigned long long)DB_NOTE_ROWS; ++i) {
+            const unsigned long long* r = x + 1 + i * 4;
+            long lane = -1, off = -1;
+            for (int l = 0; l < MAX_DECODE_LANES; ++l) {
+                const long o = g_lane[l].ll ? (long)((const uint2*)r[1] - g_lane[l].ll) : -1;
+                if (o >= 0 && o < (long)db_ll_words(S().d, S().H)) { lane = l; off = o; }
+            }
+            const std::vector<long> key = {lane, (long)(r[0] & 0xffff), (long)(r[0] >> 32 & 0xffff)};
+            auto it = rows.find(key);
+            if (it == rows.end() || (unsigned long long)off < it->second[0]) rows[key] = {(unsigned long long)off, r[0] >> 16 & 0xffff, r[2], r[3]};
+        }
+        for (auto& kv : rows)
+            fprintf(stderr, "[whisper_b200] long wait: lane %ld CTA %ld where %ld thread %llu: LL word %llu holds payload 0x%08x epoch %u, expected epoch %u\n", kv.first[0],
+                    kv.first[1], kv.first[2], kv.second[1], kv.second[0], (unsigned)kv.second[2], (unsigned)(kv.second[2] >> 32), (unsigned)kv.second[3]);
+    }
     const unsigned* p = db_fault_progress();
     for (int lane = 0; p && lane < 8; ++lane) {
         std::string line;
         char buf[48];
         for (int c = 0; c < DB_PROGRESS_LD; ++c) {
-            const unsigned v = p[lane * DB_PROGRESS_LD + c];
+            const unsigned v = p[(lane * DB_PROGRESS_LD + c) * 2], v1 = p[(lane * DB_PROGRESS_LD + c) * 2 + 1];
             if (!v) continue;
-            snprintf(buf, sizeof buf, " %d:%d/%d", c, (int)(v & 0xffff) - 1, (int)(v >> 16) - 1);
+            snprintf(buf, sizeof buf, " %d:%d,%d/%d", c, (int)(v & 0xffff) - 1, (int)(v1 & 0xffff) - 1, (int)(v >> 16) - 1);
             line += buf;
         }
-        if (!line.empty()) fprintf(stderr, "[whisper_b200] lane %d progress (CTA:consumer stage/producer stage):%s\n", lane, line.c_str());
+        if (!line.empty()) fprintf(stderr, "[whisper_b200] lane %d progress (CTA:stage of tile group 0,1/producer):%s\n", lane, line.c_str());
     }
 }
 void batch_set_model(const DbModel& m) { g_db_model_set = true; db_set_model(m); batch_clear_graphs(); }

@@ -102,7 +102,7 @@ __device__ unsigned long long* g_db_fault = nullptr;
 // wait that gives up copies the table behind the fault word, so the log shows which CTA the others were waiting for.
 __device__ unsigned g_db_progress[DB_PROGRESS_WORDS];
 __device__ __forceinline__ void db_progress(int lane_id, int half, int it) {
-    reinterpret_cast<volatile unsigned short*>(g_db_progress + lane_id * DB_PROGRESS_LD + blockIdx.x)[half] = (unsigned short)(it + 1);
+    reinterpret_cast<volatile unsigned short*>(g_db_progress + (lane_id * DB_PROGRESS_LD + blockIdx.x) * 2)[half] = (unsigned short)(it + 1);
 }
 // The consumers' version is a real function (the table copy inlined at a dozen wait sites cost 2 % of the step: the kernel is
 // instruction-fetch bound); the producer's stays one store + trap, because a call reachable from BOTH role branches makes ptxas
@@ -128,7 +128,7 @@ template <bool PRODUCER = false>
 __device__ __forceinline__ void db_wait(uint64_t* bar, uint32_t parity, int where) {         // bounded mbarrier wait
     unsigned spins = 0;
     while (!mbar_try_wait(bar, parity))
-        if (++spins > (1u << 24)) { if (PRODUCER) db_timeout_producer(where); else db_timeout(where); }
+        if (++spins > (1u << 21)) { if (PRODUCER) db_timeout_producer(where); else db_timeout(where); }
 }
 
 __device__ __forceinline__ unsigned long long db_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
@@ -161,10 +161,36 @@ __device__ __forceinline__ void ll_pause(unsigned& spins, int where) {
     if (++spins > DB_SPIN_LIMIT) db_timeout(where);
     if (spins > 48) __nanosleep(64);                  // the first polls spin: __nanosleep's granularity is coarser than an L2 round trip
 }
+// A wait for an LL word that has used half of its budget notes {CTA, thread, where | address | last value | epoch expected} in a
+// table (every long waiter does, the root cause among them); the wait that finally gives up copies the table behind the
+// progress marks.
+__device__ unsigned long long g_db_notes[DB_NOTE_ROWS * 4];
+__device__ unsigned g_db_n_notes;
+__device__ __noinline__ void db_note_wait(int where, const uint2* p, u64 v, uint32_t epoch) {
+    const unsigned i = atomicAdd(&g_db_n_notes, 1u);
+    if (i < (unsigned)DB_NOTE_ROWS) {
+        volatile unsigned long long* x = g_db_notes + i * 4;
+        x[0] = (unsigned long long)blockIdx.x | (unsigned long long)threadIdx.x << 16 | (unsigned long long)where << 32 | (unsigned long long)gridDim.x << 48;
+        x[1] = (unsigned long long)p; x[2] = v; x[3] = epoch;
+    }
+}
+__device__ __noinline__ void db_timeout_word(int where, const uint2* p, u64 v, uint32_t epoch) {
+    if (g_db_fault) {
+        volatile unsigned long long* x = g_db_fault + 2 + DB_PROGRESS_WORDS / 2;
+        const unsigned n = min(*(volatile unsigned*)&g_db_n_notes, (unsigned)DB_NOTE_ROWS);
+        for (unsigned i = 0; i < n * 4; ++i) x[1 + i] = ((volatile unsigned long long*)g_db_notes)[i];
+        x[0] = n;
+    }
+    db_timeout(where);
+}
 __device__ __forceinline__ uint32_t ll_wait_word(const uint2* p, uint32_t epoch, int where) {
     u64 v;
     unsigned spins = 0;
-    while (!ll_good(v = ll_ld1(p), epoch)) ll_pause(spins, where);
+    while (!ll_good(v = ll_ld1(p), epoch)) {
+        if (++spins > DB_SPIN_LIMIT) db_timeout_word(where, p, v, epoch);
+        if (spins == DB_SPIN_LIMIT / 2) db_note_wait(where, p, v, epoch);
+        if (spins > 48) __nanosleep(64);
+    }
     return (uint32_t)v;
 }
 // wait for the last word of every `stride`-word group in [word0, word0 + n_words) of rows [row_lo, row_hi) of an LL matrix
@@ -249,7 +275,7 @@ struct DbSmem {
 };
 __device__ __forceinline__ void db_seen_wait(const DbSmem& sm, const DbRing& ring) {
     unsigned spins = 0;
-    while (sm.seen[ring.slot] < ring.use - ring.n) if (++spins > (1u << 26)) db_timeout(26);
+    while (sm.seen[ring.slot] < ring.use - ring.n) if (++spins > (1u << 23)) db_timeout(26);
 }
 // row r of the step -> index of its token history / slot-table row / physical KV slot
 __device__ __forceinline__ int db_trow(const DbArgs& a, int r) { const int w = r / a.nbw; return w * a.slot_stride + (r - w * a.nbw); }
@@ -619,6 +645,7 @@ __device__ __forceinline__ void db_stage_self_attn(const DbSmem& sm, const DbArg
     using C = DbCfg<NT, CW>;
     const DbModel& M = c_db;
     const int d = M.d, H = M.H, tid = warp * 32 + lane, cap = a.sa_cap;
+    if ((cta + rot) % nctas >= R * H) csync<C::CONS>();    // every stage passes a CTA-wide barrier, units or not (see the stage loop)
     for (int u = (cta + rot) % nctas; u < R * H; u += nctas) {
         const int r = u / H, h = u - r * H, trow = db_trow(a, r), pos = sm.spos[r / a.nbw];
         float* ss = sm.sp;                          // [<= 449] scores
@@ -976,7 +1003,7 @@ __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsig
     for (int it = 0; it < n_stages; ++it) {
         const int l = it >> 3, st = it == M.Ld * 8 ? DBS_VOCAB : (it & 7);
         const uint32_t ep = seq * 64u + (uint32_t)l + 1u, ep_prev = ep - 1u;      // ep_prev: x3 of the layer below
-        if (tid == 0) db_progress(a.lane_id, 0, it);
+        if ((tid & 127) == 0) db_progress(a.lane_id, tid == 0 ? 0 : 2, it);       // the leaders of the two tile groups
         if (st == DBS_QKV && l < M.Ld) {
             // Hide DRAM latency: the layer's bias vectors (read by every tile's epilogue) and the cached K / V rows of the
             // self-attention units this CTA will run two stages from now were last touched a step (360 MB of traffic) ago, so
@@ -1013,7 +1040,11 @@ __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsig
             continue;
         }
         dbg.set_sub(it == a.dbg_stage ? it : -1);
-        DbStageSm& D = sm.desc[it & 1];                // (stage it - 2 is long finished: the prologue barrier of it - 1 lies between)
+        // (double-buffered: a group may still be in the epilogue of stage it - 1's last tile.  Stage it - 2 is finished: EVERY stage
+        // passes at least one CTA-wide barrier - a CTA without a tile or an attention unit in a stage too, or thread 0 could
+        // refill this descriptor while the other group's last tile of stage it - 2 still reads it and stores its outputs through
+        // the wrong pointers: the rare hang of the prompt launches, where only 20 CTAs have a self-attention unit)
+        DbStageSm& D = sm.desc[it & 1];
         if (tid == 0) {
             const DbGemv q{st, l < M.Ld ? l : 0, 0, 0, 0, ep, 0};
             D.bias = q.bias(); D.res_ll = q.res_ll(a); D.out_ll = q.out_ll(a); D.out_llb = q.out_llb(a); D.ld_out = q.ld_out(a);
@@ -1024,6 +1055,7 @@ __device__ __forceinline__ void db_consumer(const DbArgs& a, uint8_t* raw, unsig
             const DbStageDesc sd = db_stage_desc(st, l < M.Ld ? l : 0, cta, nctas);
             int u0, u1;
             db_range(sd.n_tiles, sd.vcta, nctas, u0, u1);
+            if (u1 <= u0 && st != DBS_M2) csync<C::CONS>();
             if (u1 > u0 && st != DBS_M2) {             // a CTA without a tile in this stage does not read its input at all
                 if (sd.ln_g) {
                     const uint2* src = st == DBS_CQ ? a.ll_x1b : st == DBS_M1 ? a.ll_x2b : a.ll_x3b;
@@ -1092,8 +1124,8 @@ __global__ void __launch_bounds__(DbCfg<NT, CW>::THREADS, 1) decoder_batch_kerne
 static unsigned long long* g_h_fault = nullptr;
 void db_set_model(const DbModel& m) {
     B200_CHECK(cudaMemcpyToSymbol(c_db, &m, sizeof(DbModel)));
-    if (!g_h_fault && cudaHostAlloc((void**)&g_h_fault, 16 + DB_PROGRESS_WORDS * 4, cudaHostAllocMapped) == cudaSuccess) {
-        memset(g_h_fault, 0, 16 + DB_PROGRESS_WORDS * 4);
+    if (!g_h_fault && cudaHostAlloc((void**)&g_h_fault, 16 + DB_PROGRESS_WORDS * 4 + 8 + DB_NOTE_ROWS * 32, cudaHostAllocMapped) == cudaSuccess) {
+        memset(g_h_fault, 0, 16 + DB_PROGRESS_WORDS * 4 + 8 + DB_NOTE_ROWS * 32);
         unsigned long long* dp = nullptr;
         if (cudaHostGetDevicePointer((void**)&dp, g_h_fault, 0) == cudaSuccess) B200_CHECK(cudaMemcpyToSymbol(g_db_fault, &dp, sizeof(dp)));
     }
@@ -1101,8 +1133,10 @@ void db_set_model(const DbModel& m) {
 // {where, grid, CTA, thread} of the bounded wait that trapped (0 = none): decoder_batch.cu's `where` codes are 2..13 for LL polls,
 // 20..25 for consumer waits on a ring slot, 30..33 for the producer's waits on a free slot
 unsigned long long db_fault_word() { return g_h_fault ? *(volatile unsigned long long*)g_h_fault : 0ull; }
-// progress table saved with the fault word: [decode lane][DB_PROGRESS_LD] of (consumer stage + 1) | (producer stage + 1) << 16
+// progress table saved with the fault word: [decode lane][DB_PROGRESS_LD][4] 16-bit marks: (stage + 1) of tile group 0, the producer, tile group 1
 const unsigned* db_fault_progress() { return g_h_fault ? reinterpret_cast<const unsigned*>(g_h_fault + 2) : nullptr; }
+// [0] = n, then n rows {CTA | thread << 16 | where << 32 | grid << 48, address, last value read, epoch expected}: the LL word waits that were long
+const unsigned long long* db_fault_ll_word() { return g_h_fault ? g_h_fault + 2 + DB_PROGRESS_WORDS / 2 : nullptr; }
 
 int db_consumer_warps() {
     return 8;

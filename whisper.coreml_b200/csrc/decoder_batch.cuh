@@ -11,7 +11,8 @@ constexpr int DB_MAX_LAYERS = 32;
 constexpr int DB_MAX_WINDOWS = 8;        // windows per batched step (each with its own cross K/V, KV cache rows and decode state)
 constexpr int DB_MAX_ROWS = 40;          // rows = windows x beams per step: 5 n-tiles of mma.m16n8k16
 constexpr int DB_DBG_LD = 640;           // timeline marks per CTA (2 per stage + 1)
-constexpr int DB_PROGRESS_LD = 160, DB_PROGRESS_WORDS = 8 * DB_PROGRESS_LD;    // progress words: [decode lane][CTA]
+constexpr int DB_NOTE_ROWS = 256;         // long LL-word waits noted for the fault report
+constexpr int DB_PROGRESS_LD = 160, DB_PROGRESS_WORDS = 8 * DB_PROGRESS_LD * 2; // progress: [decode lane][CTA][4] 16-bit marks (group 0, producer, group 1, -)
 constexpr int DB_N_SPLITS = 7;           // key splits of a cross-attention head (224 keys each)
 
 struct DbLayer {
@@ -63,6 +64,7 @@ size_t db_ll_words(size_t d, size_t H);
 void db_carve_ll(DbArgs& a, uint2* base, size_t d, size_t H);
 bool db_launch(const DbArgs& a, int n_ctas, cudaStream_t s);
 const unsigned* db_fault_progress();
+const unsigned long long* db_fault_ll_word();
 unsigned long long db_fault_word();                     // what the kernel left before a timeout trap (0 = nothing)
 
 }  // namespace b200
