@@ -75,7 +75,10 @@ void decoder1Predict(
 
 /* Errors: Part 1 keeps the reference's `void` signatures (coreml.mm logs and continues);
  * failures are also recorded here.  Returns the number of errors since the last call and
- * copies the most recent message. */
+ * copies the most recent message.  Every message is also written to stderr as it happens; a
+ * bounded wait of the persistent step kernel that gives up (a protocol bug, never a normal
+ * condition) additionally logs which wait, the stage every CTA had reached and the words the
+ * long waits were polling (csrc/decoder_batch.cu: db_fault_word). */
 int  b200LastError(char* buf, int buf_len);
 /* Select the CUDA device (default 0) before any load*.  One process drives one GPU. */
 void b200SetDevice(int device);
