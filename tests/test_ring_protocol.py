@@ -108,3 +108,48 @@ def test_a_waiter_that_does_not_release_can_wait_forever():
     owners = _schedule_single_slot_tiles()
     outcomes = {simulate(owners, 2, "both-wait", random.Random(seed), max_ticks=20000) for seed in range(400)}
     assert "deadlock" in outcomes, outcomes
+
+
+# ---- the double-buffered stage descriptor ---------------------------------------------------------------------------------
+def simulate_descriptor(has_barrier, rng, max_ticks=20000):
+    """Thread 0 (in group 0) writes desc[it & 1] at the top of stage `it`; every group reads desc[it & 1] when it stores the outputs
+    of its last tile of stage `it`.  has_barrier[it]: the stage passes a CTA-wide barrier (after the descriptor write).  Returns
+    'ok' or 'stale' (a group stored stage it's outputs through another stage's descriptor)."""
+    n = len(has_barrier)
+    desc = [None, None]
+    # per group: (stage, point) with point 0 = stage top, 1 = at the barrier, 2 = storing outputs
+    st = [[0, 0], [0, 0]]
+    for _ in range(max_ticks):
+        if all(s[0] >= n for s in st):
+            return "ok"
+        g = rng.randrange(2)
+        it, point = st[g]
+        if it >= n:
+            continue
+        if point == 0:
+            if g == 0:
+                desc[it & 1] = it
+            st[g][1] = 1
+        elif point == 1:
+            other = st[1 - g]
+            if has_barrier[it] and not (other[0] > it or (other[0] == it and other[1] >= 1)):
+                continue                                             # wait at the barrier for the other group
+            st[g][1] = 2
+        else:
+            if desc[it & 1] != it:
+                return "stale"
+            st[g] = [it + 1, 0]
+    return "ok"
+
+
+def test_one_barrier_per_stage_keeps_the_descriptor_valid():
+    for seed in range(500):
+        assert simulate_descriptor([True] * 12, random.Random(seed)) == "ok", seed
+
+
+def test_a_stage_without_a_barrier_lets_the_descriptor_be_overwritten():
+    """The prompt launches before the fix: a CTA without a self-attention unit had no barrier in stage 1."""
+    has = [True] * 12
+    has[1] = False
+    outcomes = {simulate_descriptor(has, random.Random(seed)) for seed in range(500)}
+    assert "stale" in outcomes, outcomes
