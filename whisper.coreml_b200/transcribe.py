@@ -126,7 +126,7 @@ def transcribe(model, audio: torch.Tensor, *, beam_size: Optional[int] = 5, best
         raise ValueError(f"seek_mode {seek_mode!r}: 'fixed' or 'reference'")
     model.load()
     dims, sp = model.dims, model.specials
-    dev = f"cuda:{model.device_index}"
+    dev = getattr(model, "device", None) or f"cuda:{model.device_index}"    # (tests/test_fallback_ladder.py drives the host logic with a scripted backend)
     mel = log_mel_spectrogram(audio.to(dev), dims.n_mels, padding=N_SAMPLES)          # transcribe.py:143 (global max per file)
     content_frames = mel.shape[-1] - N_FRAMES
     temperatures = [float(temperature)] if isinstance(temperature, (int, float)) else [float(t) for t in temperature]
@@ -188,8 +188,16 @@ def transcribe(model, audio: torch.Tensor, *, beam_size: Optional[int] = 5, best
         """segments (+ words, text) of one decoded window and the seek the reference continues from (host only)"""
         r, seek, segment_size = win.result, win.seek, win.segment_size
         time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
-        if skipped(r) or not r.tokens:
+        if skipped(r):
             return [], seek + segment_size
+        if not r.tokens:                           # nothing decoded: the reference still reports the (empty) window as one segment
+            cur = [{"seek": seek, "start": time_offset, "end": time_offset + segment_size * HOP_LENGTH / SAMPLE_RATE, "tokens": [],
+                    "temperature": r.temperature, "avg_logprob": r.avg_logprob, "no_speech_prob": r.no_speech_prob}]
+            if tokenizer is not None:
+                cur[0]["text"] = ""
+            if word_timestamps:
+                cur[0]["words"] = []
+            return cur, seek + segment_size
         cur = _segments_from_tokens(r.tokens, r, time_offset, segment_size * HOP_LENGTH / SAMPLE_RATE, seek, sp.timestamp_begin,
                                     seek_mode == "fixed")
         nxt = _next_seek(r.tokens, seek, segment_size, sp.timestamp_begin)
@@ -226,6 +234,12 @@ def transcribe(model, audio: torch.Tensor, *, beam_size: Optional[int] = 5, best
         if verbose:
             for s in cur:
                 print(f"[{s['start']:.2f} --> {s['end']:.2f}] {len(s['tokens'])} tokens")
+        if tokenizer is not None:                  # "if a segment is instantaneous or does not contain text, clear it" (:495-500);
+            for s in cur:                          # without a tokenizer the caller gets the raw token segments
+                if s["start"] == s["end"] or s["text"].strip() == "":
+                    s["text"], s["tokens"] = "", []
+                    if "words" in s:
+                        s["words"] = []
         return cur, nxt
 
     def exchange(mine: List[_Window]) -> Dict[int, _Window]:
